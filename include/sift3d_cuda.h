@@ -1,0 +1,147 @@
+/* sift3d_cuda.h -- C ABI of the B200 device engine (libsift3d_cuda.so).
+ *
+ * This is the thin shim the host library (libsift3D.so, plain C) calls.  Every
+ * entry point takes plain pointers and sizes; no C++/torch types cross it.  Each
+ * function names the reference routine whose work it replaces (file:line in
+ * bbrister/SIFT3D v1.4.6) -- the reference has no FFI of its own for this path
+ * (single process, host memory only), so "what its FFI would bind" is exactly
+ * the set of internal calls SIFT3D_detect_keypoints / SIFT3D_extract_descriptors /
+ * SIFT3D_extract_dense_descriptors make into imutil.c and sift.c.
+ *
+ * Conventions: every function returns 0 on success and -1 on failure (the
+ * reference's SIFT3D_SUCCESS / SIFT3D_FAILURE, imtypes.h:20-22); the message is
+ * available from s3d_engine_error().  Volumes are [z][y][x] float32, x fastest
+ * (SIFT3D_IM_GET_IDX, immacros.h:58-59).  There is NO CPU fallback: if no CUDA
+ * device is usable, s3d_engine_create fails.
+ */
+#ifndef SIFT3D_CUDA_H
+#define SIFT3D_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_DESC_NUMEL 768   /* 4^3 spatial cells x 12 icosahedron vertices (imtypes.h:79-98) */
+#define S3D_DESC_STRIDE 3104 /* sizeof(SIFT3D_Descriptor): 768 f32 + xd,yd,zd,sd f64 */
+#define S3D_MAX_TAPS 129     /* widest separable filter accepted (half width 64) */
+
+typedef struct s3d_engine s3d_engine;
+
+/* Geometry of one pyramid level (the metadata half of `Image`, imtypes.h:156-168). */
+typedef struct s3d_geom {
+    int nx, ny, nz;
+    double ux, uy, uz; /* physical units of a voxel */
+    double scale;      /* absolute scale s of the level (Image.s) */
+} s3d_geom;
+
+/* One separable FIR filter (Sep_FIR_filter, imtypes.h:171-179); taps on the host. */
+typedef struct s3d_filter {
+    const float *taps;
+    int width;
+} s3d_filter;
+
+/* Keypoint record exchanged with the host (the data half of `Keypoint`,
+ * imtypes.h:253-261).  x,y,z are the f32 centre the reference uses
+ * (`Cvec vcenter = {key->xd, ...}`, sift.c:1280 and sift.c:1866-1868). */
+typedef struct s3d_keypoint {
+    float R[9]; /* row-major */
+    float x, y, z;
+    double sd;
+    int o, s;
+} s3d_keypoint; /* 64 bytes */
+
+/* ---- lifecycle ------------------------------------------------------------ */
+/* device < 0: use $SIFT3D_CUDA_DEVICE, else $LOCAL_RANK, else 0. */
+int s3d_engine_create(s3d_engine **out, int device);
+void s3d_engine_destroy(s3d_engine *e);
+const char *s3d_engine_error(const s3d_engine *e);
+const char *s3d_last_create_error(void);
+int s3d_engine_device(const s3d_engine *e);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) so the
+ * caller's CUDA events bracket the kernels.  NULL restores the engine's own. */
+int s3d_engine_set_stream(s3d_engine *e, void *cuda_stream);
+void *s3d_engine_stream(const s3d_engine *e);
+int s3d_engine_sync(s3d_engine *e);
+/* Number of kernels this engine has launched since creation (bench: gpu_launches). */
+long long s3d_engine_launch_count(const s3d_engine *e);
+
+/* Icosahedron table exactly as init_geometry builds it (sift.c:215-326):
+ * v[20][3][3] vertex vectors (after the reference's vertex swap), idx[20][3]. */
+int s3d_set_mesh(s3d_engine *e, const float *v, const int *idx);
+
+/* ---- pyramid (replaces resize_Pyramid imutil.c:3858, make_gss imutil.c:3752) --- */
+/* gpyr: num_octaves*(K+3) levels, dog: num_octaves*(K+2) levels, octave-major,
+ * first level s = -1.  Allocates HBM for every level. */
+int s3d_pyramid_resize(s3d_engine *e, int num_octaves, int num_kp_levels,
+                       const s3d_geom *gpyr, const s3d_geom *dog);
+/* first: sigma_n -> s(0,-1); octave[j]: level j-1 -> j (sift.c:1012,1020). */
+int s3d_pyramid_filters(s3d_engine *e, const s3d_filter *first, const s3d_filter *octave,
+                        int num_octave_filters);
+
+/* im_copy_data (imutil.c:1895): host image with element strides -> HBM. */
+int s3d_image_upload(s3d_engine *e, const float *host, int nx, int ny, int nz, size_t xs,
+                     size_t ys, size_t zs);
+/* Same, source already resident in HBM (contiguous). */
+int s3d_image_from_device(s3d_engine *e, const float *dev, int nx, int ny, int nz);
+
+/* im_scale (imutil.c:1977) + build_gpyr (sift.c:989) + build_dog (sift.c:1052). */
+int s3d_build_pyramid(s3d_engine *e);
+/* detect_extrema (sift.c:1074): candidates stay on the device, in scan order. */
+int s3d_detect_extrema(s3d_engine *e, double peak_thresh, int *num_candidates);
+/* assign_orientations (sift.c:1264): rejects + stable compaction. */
+int s3d_assign_orientations(s3d_engine *e, double corner_thresh, int *num_keypoints);
+int s3d_candidates_download(s3d_engine *e, s3d_keypoint *out, int cap);
+int s3d_keypoints_download(s3d_engine *e, s3d_keypoint *out, int cap);
+
+/* _SIFT3D_extract_descriptors (sift.c:2207) on the resident Gaussian pyramid.
+ * host_desc: n records of S3D_DESC_STRIDE bytes (the SIFT3D_Descriptor layout). */
+int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *host_desc);
+/* Same with device-resident keypoints/descriptors (bench: no PCIe in the timed region). */
+int s3d_extract_descriptors_device(s3d_engine *e, const s3d_keypoint *dev_kp, int n,
+                                   void *dev_desc);
+/* Keypoints left on the device by s3d_assign_orientations (for the above). */
+const s3d_keypoint *s3d_device_keypoints(const s3d_engine *e);
+
+/* One-level pyramid for the raw-image entry points (sift.c:2131-2195, 1534-1604):
+ * uploads the image, applies smooth_scale_raw_input (sift.c:1978-2006) and leaves
+ * the result as level (o=0, s=0) with absolute scale `scale`. */
+int s3d_single_level(s3d_engine *e, const float *host, int nx, int ny, int nz, size_t xs, size_t ys,
+                     size_t zs, const double units[3], double scale, const s3d_filter *smooth);
+/* assign_eig_ori (sift.c:1354) on host-supplied keypoints: sigma = sig_fctr * kp.sd.
+ * Fills kp[i].R; ok[i] = 0 where the reference returns REJECT (incl. conf < thresh);
+ * conf[i] = corner score (0 on reject before the score exists). */
+int s3d_orient_keypoints(s3d_engine *e, s3d_keypoint *kp, int n, double sig_fctr,
+                         double corner_thresh, double *conf, unsigned char *ok);
+
+/* SIFT3D_extract_dense_descriptors, dense_rotate = 0 (sift.c:2354-2496).
+ * smooth: sigma_n -> sigma0 filter; window: the 12-channel blur filter;
+ * units: of the input image; desc_units: of the caller's `desc` Image (the
+ * reference blurs the channel image in THOSE units, sift.c:2451).
+ * host_out: nx*ny*nz*12 floats, channel-interleaved. */
+int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, int nz, size_t xs,
+                          size_t ys, size_t zs, const double units[3],
+                          const double desc_units[3], const s3d_filter *smooth,
+                          const s3d_filter *window, float *host_out);
+
+/* Host copy of a pyramid level (which: 0 = Gaussian, 1 = DoG). */
+int s3d_level_download(s3d_engine *e, int which, int o, int s, float *host_dst);
+int s3d_pyramid_copy(s3d_engine *dst, const s3d_engine *src); /* copy_Pyramid, imutil.c:3995 */
+int s3d_num_octaves(const s3d_engine *e);
+
+/* ---- kernel-level entry (tests / bench roofline): device pointers ------------ */
+/* apply_Sep_FIR_filter (imutil.c:3459): x, y, z passes, nc interleaved channels. */
+int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx, int ny, int nz,
+                    int nc, const float *taps, int width, double unit, const double units[3]);
+/* 0 = auto (fused fast path when eligible), 1 = force the generic per-axis path. */
+int s3d_set_blur_mode(s3d_engine *e, int mode);
+void *s3d_dev_alloc(s3d_engine *e, size_t bytes);
+void s3d_dev_free(s3d_engine *e, void *p);
+int s3d_memcpy_h2d(s3d_engine *e, void *dev, const void *host, size_t bytes);
+int s3d_memcpy_d2h(s3d_engine *e, void *host, const void *dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -199,9 +199,10 @@ void orc_mesh(float *vout, int *idxout)
             v[j][1] = vert[3 * id + 1];
             v[j][2] = vert[3 * id + 2];
             mag = sqrtf(v[j][0] * v[j][0] + v[j][1] * v[j][1] + v[j][2] * v[j][2]);
-            v[j][0] = v[j][0] * (1.0f / mag);
-            v[j][1] = v[j][1] * (1.0f / mag);
-            v[j][2] = v[j][2] * (1.0f / mag);
+            /* SIFT3D_CVEC_SCALE(v + j, 1.0f / mag) expands to x * 1.0f / mag (sift.c:295) */
+            v[j][0] = v[j][0] * 1.0f / mag;
+            v[j][1] = v[j][1] * 1.0f / mag;
+            v[j][2] = v[j][2] * 1.0f / mag;
         }
         for (j = 0; j < 3; j++) {
             t1[j] = v[2][j] - v[1][j];

@@ -1,0 +1,139 @@
+// common.cuh -- shared declarations of the B200 SIFT3D device engine.
+//
+// All arithmetic that feeds a parity-checked result is written with explicit
+// round-to-nearest intrinsics (__fmul_rn/__fadd_rn/...) and the whole library is
+// compiled with -fmad=false: the reference is built for baseline x86-64 (no FMA),
+// so every multiply and add there rounds separately.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/sift3d_cuda.h"
+
+#define S3D_NUM_SMS_FALLBACK 148
+
+struct TapSet {  // passed by value as a kernel parameter (lands in the constant bank)
+    float t[S3D_MAX_TAPS];
+    int width;
+};
+
+struct LevelDev {
+    s3d_geom g;
+    float *d = nullptr;
+    size_t n() const { return (size_t)g.nx * g.ny * g.nz; }
+};
+
+struct Candidate {  // 16 bytes, device-side candidate / keypoint coordinate record
+    short o, s;
+    int x, y, z;
+};
+
+// per-face constants of the Moller-Trumbore test, derived once from the mesh in
+// the reference's f32 operation order (cart2bary, sift.c:335-394)
+struct FaceConst {
+    float e1[3], e2[3], t[3], q[3];
+    float e2q;
+    int idx[3];
+    float vmid[3];  // unit centroid direction (fast-path preselection only)
+};
+
+struct MeshDev {
+    FaceConst f[20];
+    float vert[12][3];  // unit vertex directions (fast-path preselection only)
+};
+
+struct s3d_engine {
+    int device = 0;
+    int num_sms = S3D_NUM_SMS_FALLBACK;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    int blur_mode = 0;
+
+    // pyramid
+    int noct = 0, K = 0, nlev_g = 0, nlev_d = 0;
+    int first_level = -1;  // index of the first level of an octave (-1 for detector pyramids)
+    std::vector<LevelDev> g, dog;
+    TapSet first_taps{};
+    std::vector<TapSet> oct_taps;
+    float *im = nullptr;  // scaled input copy (sift3d->im)
+    int im_nx = 0, im_ny = 0, im_nz = 0;
+    size_t im_cap = 0;
+    float *scratch[2] = {nullptr, nullptr};
+    size_t scratch_cap = 0;
+    unsigned *d_scalars = nullptr;  // [0] = image max bits, [1 + o*nlev_d + (s+1)] = dogmax bits
+    int n_scalars = 0;
+
+    // extrema / keypoints
+    Candidate *d_cand = nullptr;
+    int cand_cap = 0;
+    int ncand = 0;
+    unsigned *d_mask = nullptr;  // bit masks, per keypoint level of the current octave
+    size_t mask_cap = 0;
+    int *d_blockcnt = nullptr;
+    size_t blockcnt_cap = 0;
+    int *d_counter = nullptr;  // [0] running candidate total, [1] keypoint total
+    s3d_keypoint *d_kp_all = nullptr;  // candidates as keypoint records (R filled by k_orient)
+    double *d_conf = nullptr;
+    unsigned char *d_ok = nullptr;
+    int *d_pos = nullptr;
+    s3d_keypoint *d_kp = nullptr;  // compacted keypoints
+    int kp_cap = 0;
+    int nkp = 0;
+
+    // descriptor scratch
+    s3d_keypoint *d_kp_in = nullptr;
+    int kp_in_cap = 0;
+    unsigned char *d_desc = nullptr;
+    size_t desc_cap = 0;
+
+    MeshDev *d_mesh = nullptr;
+    bool have_mesh = false;
+    float **d_level_ptrs = nullptr;  // device table of gpyr level pointers
+    int *d_level_dims = nullptr;     // nx,ny,nz per gpyr level
+    float *d_level_units = nullptr;  // (float)ux,uy,uz per gpyr level
+    double *d_level_scales = nullptr;  // Image.s per gpyr level
+};
+
+int s3d_fail(s3d_engine *e, const char *what, cudaError_t ce, const char *file, int line);
+
+#define S3D_CUDA(e, call)                                                     \
+    do {                                                                      \
+        cudaError_t _ce = (call);                                             \
+        if (_ce != cudaSuccess) return s3d_fail((e), #call, _ce, __FILE__, __LINE__); \
+    } while (0)
+
+#define S3D_LAUNCH_CHECK(e)                                                   \
+    do {                                                                      \
+        (e)->launches++;                                                      \
+        cudaError_t _ce = cudaGetLastError();                                 \
+        if (_ce != cudaSuccess) return s3d_fail((e), "kernel launch", _ce, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- launchers implemented in pyramid.cu ------------------------------------
+int s3d_k_max_abs(s3d_engine *e, const float *x, size_t n, unsigned *d_bits);
+int s3d_k_scale(s3d_engine *e, const float *src, float *dst, size_t n, const unsigned *d_bits);
+int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz, int nc,
+               const TapSet &taps, const float uf[3]);
+int s3d_k_decimate(s3d_engine *e, const float *src, int sx, int sy, int sz, float *dst, int dx,
+                   int dy, int dz);
+int s3d_k_dog(s3d_engine *e, const float *a, const float *b, float *d, size_t n,
+              unsigned *d_maxbits);
+int s3d_k_extrema_octave(s3d_engine *e, int o, float peak_thresh_dummy, double peak_thresh);
+int s3d_ensure_scratch(s3d_engine *e, size_t elems);
+
+// ---- launchers implemented in keypoint.cu -----------------------------------
+int s3d_k_orientations(s3d_engine *e, double corner_thresh);
+int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
+                      double corner_thresh, unsigned char *d_ok, double *d_conf);
+int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out);
+int s3d_k_dense(s3d_engine *e, const float *d_smooth, const float *d_raw, int nx, int ny, int nz,
+                const float inv_units[3], float *d_temp12);
+int s3d_k_dense_post(s3d_engine *e, float *d_desc12, const float *d_raw, size_t nvox);
+int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx);

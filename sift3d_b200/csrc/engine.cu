@@ -1,0 +1,711 @@
+// engine.cu -- the C-ABI of libsift3d_cuda.so (see include/sift3d_cuda.h).
+//
+// One engine = one CUDA device + one stream + the HBM-resident pyramids of one
+// SIFT3D object.  Host code (plain C, sift3d_b200/host/) owns parameters, filter
+// design and the reference-compatible structs; everything per-voxel happens here.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+static thread_local std::string g_create_err;
+
+int s3d_fail(s3d_engine *e, const char *what, cudaError_t ce, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "sift3d_cuda: %s failed: %s (%s:%d)", what,
+             ce == cudaSuccess ? "invalid state/argument" : cudaGetErrorString(ce), file, line);
+    if (e) e->err = buf;
+    g_create_err = buf;
+    fprintf(stderr, "%s\n", buf);
+    return -1;
+}
+
+int s3d_pack_candidates(s3d_engine *e, s3d_keypoint *d_out);  // keypoint.cu
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+void free_pyramid(s3d_engine *e)
+{
+    for (auto &l : e->g)
+        if (l.d) cudaFree(l.d);
+    for (auto &l : e->dog)
+        if (l.d) cudaFree(l.d);
+    e->g.clear();
+    e->dog.clear();
+    if (e->d_level_ptrs) cudaFree(e->d_level_ptrs);
+    if (e->d_level_dims) cudaFree(e->d_level_dims);
+    if (e->d_level_units) cudaFree(e->d_level_units);
+    if (e->d_level_scales) cudaFree(e->d_level_scales);
+    if (e->d_scalars) cudaFree(e->d_scalars);
+    e->d_level_ptrs = nullptr;
+    e->d_level_dims = nullptr;
+    e->d_level_units = nullptr;
+    e->d_level_scales = nullptr;
+    e->d_scalars = nullptr;
+    e->noct = 0;
+}
+
+int ensure_cand(s3d_engine *e, int cap)
+{
+    if (cap <= e->cand_cap) return 0;
+    if (e->d_cand) cudaFree(e->d_cand);
+    if (e->d_kp_all) cudaFree(e->d_kp_all);
+    if (e->d_ok) cudaFree(e->d_ok);
+    if (e->d_pos) cudaFree(e->d_pos);
+    if (e->d_kp) cudaFree(e->d_kp);
+    e->d_cand = nullptr;
+    e->d_kp_all = nullptr;
+    e->d_ok = nullptr;
+    e->d_pos = nullptr;
+    e->d_kp = nullptr;
+    e->cand_cap = 0;
+    S3D_CUDA(e, cudaMalloc(&e->d_cand, (size_t)cap * sizeof(Candidate)));
+    S3D_CUDA(e, cudaMalloc(&e->d_kp_all, (size_t)cap * sizeof(s3d_keypoint)));
+    S3D_CUDA(e, cudaMalloc(&e->d_ok, (size_t)cap));
+    S3D_CUDA(e, cudaMalloc(&e->d_pos, (size_t)cap * sizeof(int)));
+    S3D_CUDA(e, cudaMalloc(&e->d_kp, (size_t)cap * sizeof(s3d_keypoint)));
+    e->cand_cap = cap;
+    e->kp_cap = cap;
+    return 0;
+}
+
+int to_tapset(s3d_engine *e, const s3d_filter *f, TapSet &t)
+{
+    if (!f || !f->taps || f->width < 1 || f->width > S3D_MAX_TAPS || !(f->width & 1))
+        return s3d_fail(e, "filter width (odd, <= S3D_MAX_TAPS)", cudaSuccess, __FILE__, __LINE__);
+    memset(&t, 0, sizeof(t));
+    memcpy(t.t, f->taps, f->width * sizeof(float));
+    t.width = f->width;
+    return 0;
+}
+
+void level_uf(const s3d_geom &g, double unit, float uf[3])
+{  // unit_factor = unit / units[dim], narrowed to f32 (imutil.c:2288-2289)
+    uf[0] = (float)(unit / g.ux);
+    uf[1] = (float)(unit / g.uy);
+    uf[2] = (float)(unit / g.uz);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *s3d_last_create_error(void) { return g_create_err.c_str(); }
+
+int s3d_engine_create(s3d_engine **out, int device)
+{
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        // No CPU fallback by design: the accelerated path IS the product.
+        s3d_fail(nullptr, "cudaGetDeviceCount (no usable CUDA device; there is no CPU fallback)",
+                 ce == cudaSuccess ? cudaErrorNoDevice : ce, __FILE__, __LINE__);
+        return -1;
+    }
+    if (device < 0) {
+        const char *env = getenv("SIFT3D_CUDA_DEVICE");
+        if (!env) env = getenv("LOCAL_RANK");
+        device = env ? atoi(env) : 0;
+        if (device < 0 || device >= ndev) device = device % ndev;
+    }
+    if (device >= ndev) {
+        s3d_fail(nullptr, "device index out of range", cudaErrorInvalidDevice, __FILE__, __LINE__);
+        return -1;
+    }
+    s3d_engine *e = new s3d_engine();
+    e->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        s3d_fail(nullptr, "cudaGetDeviceProperties", ce, __FILE__, __LINE__);
+        delete e;
+        return -1;
+    }
+    e->num_sms = prop.multiProcessorCount;
+    if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        s3d_fail(nullptr, "cudaStreamCreate", ce, __FILE__, __LINE__);
+        delete e;
+        return -1;
+    }
+    e->stream = e->own_stream;
+    if ((ce = cudaMalloc(&e->d_counter, 4 * sizeof(int))) != cudaSuccess) {
+        s3d_fail(nullptr, "cudaMalloc", ce, __FILE__, __LINE__);
+        cudaStreamDestroy(e->own_stream);
+        delete e;
+        return -1;
+    }
+    *out = e;
+    return 0;
+}
+
+void s3d_engine_destroy(s3d_engine *e)
+{
+    if (!e) return;
+    DeviceGuard guard(e->device);
+    cudaStreamSynchronize(e->stream);
+    free_pyramid(e);
+    void *ptrs[] = {e->im,    e->scratch[0], e->scratch[1], e->d_cand,  e->d_mask, e->d_blockcnt,
+                    e->d_counter, e->d_kp_all, e->d_ok,       e->d_pos,   e->d_kp,   e->d_kp_in,
+                    e->d_desc, e->d_mesh};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+const char *s3d_engine_error(const s3d_engine *e) { return e ? e->err.c_str() : ""; }
+int s3d_engine_device(const s3d_engine *e) { return e->device; }
+long long s3d_engine_launch_count(const s3d_engine *e) { return e->launches; }
+void *s3d_engine_stream(const s3d_engine *e) { return (void *)e->stream; }
+
+int s3d_engine_set_stream(s3d_engine *e, void *cuda_stream)
+{
+    DeviceGuard guard(e->device);
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+
+int s3d_engine_sync(s3d_engine *e)
+{
+    DeviceGuard guard(e->device);
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int s3d_set_blur_mode(s3d_engine *e, int mode)
+{
+    e->blur_mode = mode;
+    return 0;
+}
+
+int s3d_set_mesh(s3d_engine *e, const float *v, const int *idx)
+{
+    DeviceGuard guard(e->device);
+    return s3d_upload_mesh(e, v, idx);
+}
+
+int s3d_num_octaves(const s3d_engine *e) { return e->noct; }
+
+int s3d_pyramid_resize(s3d_engine *e, int num_octaves, int num_kp_levels, const s3d_geom *gpyr,
+                       const s3d_geom *dog)
+{
+    DeviceGuard guard(e->device);
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    const int nlev_d = num_kp_levels + 2, nlev_g = num_kp_levels + 3;
+    // keep the allocation when nothing changed
+    bool same = e->noct == num_octaves && e->K == num_kp_levels &&
+                (int)e->g.size() == num_octaves * nlev_g;
+    for (int i = 0; same && i < num_octaves * nlev_g; i++)
+        same = e->g[i].g.nx == gpyr[i].nx && e->g[i].g.ny == gpyr[i].ny && e->g[i].g.nz == gpyr[i].nz;
+    if (same) {
+        for (int i = 0; i < num_octaves * nlev_g; i++) e->g[i].g = gpyr[i];
+        for (int i = 0; i < num_octaves * nlev_d; i++) e->dog[i].g = dog[i];
+    } else {
+        free_pyramid(e);
+        e->noct = num_octaves;
+        e->K = num_kp_levels;
+        e->nlev_g = nlev_g;
+        e->nlev_d = nlev_d;
+        e->first_level = -1;
+        e->g.resize((size_t)num_octaves * nlev_g);
+        e->dog.resize((size_t)num_octaves * nlev_d);
+        for (int i = 0; i < num_octaves * nlev_g; i++) {
+            e->g[i].g = gpyr[i];
+            S3D_CUDA(e, cudaMalloc(&e->g[i].d, e->g[i].n() * sizeof(float)));
+        }
+        for (int i = 0; i < num_octaves * nlev_d; i++) {
+            e->dog[i].g = dog[i];
+            S3D_CUDA(e, cudaMalloc(&e->dog[i].d, e->dog[i].n() * sizeof(float)));
+        }
+        const int L = num_octaves * nlev_g;
+        S3D_CUDA(e, cudaMalloc(&e->d_level_ptrs, L * sizeof(float *)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_dims, 3 * L * sizeof(int)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_units, 3 * L * sizeof(float)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_scales, L * sizeof(double)));
+        e->n_scalars = 1 + num_octaves * nlev_d;
+        S3D_CUDA(e, cudaMalloc(&e->d_scalars, e->n_scalars * sizeof(unsigned)));
+    }
+    if (num_octaves == 0) return 0;
+    const int L = num_octaves * nlev_g;
+    std::vector<float *> ptrs(L);
+    std::vector<int> dims(3 * L);
+    std::vector<float> units(3 * L);
+    std::vector<double> scales(L);
+    for (int i = 0; i < L; i++) {
+        ptrs[i] = e->g[i].d;
+        dims[3 * i] = gpyr[i].nx;
+        dims[3 * i + 1] = gpyr[i].ny;
+        dims[3 * i + 2] = gpyr[i].nz;
+        units[3 * i] = (float)gpyr[i].ux;
+        units[3 * i + 1] = (float)gpyr[i].uy;
+        units[3 * i + 2] = (float)gpyr[i].uz;
+        scales[i] = gpyr[i].scale;
+    }
+    S3D_CUDA(e, cudaMemcpy(e->d_level_ptrs, ptrs.data(), L * sizeof(float *), cudaMemcpyHostToDevice));
+    S3D_CUDA(e, cudaMemcpy(e->d_level_dims, dims.data(), 3 * L * sizeof(int), cudaMemcpyHostToDevice));
+    S3D_CUDA(e, cudaMemcpy(e->d_level_units, units.data(), 3 * L * sizeof(float), cudaMemcpyHostToDevice));
+    S3D_CUDA(e, cudaMemcpy(e->d_level_scales, scales.data(), L * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int s3d_pyramid_filters(s3d_engine *e, const s3d_filter *first, const s3d_filter *octave,
+                        int num_octave_filters)
+{
+    if (to_tapset(e, first, e->first_taps)) return -1;
+    e->oct_taps.resize(num_octave_filters);
+    for (int i = 0; i < num_octave_filters; i++)
+        if (to_tapset(e, &octave[i], e->oct_taps[i])) return -1;
+    return 0;
+}
+
+static int ensure_im(s3d_engine *e, int nx, int ny, int nz)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    if (n > e->im_cap) {
+        if (e->im) cudaFree(e->im);
+        e->im = nullptr;
+        e->im_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->im, n * sizeof(float)));
+        e->im_cap = n;
+    }
+    e->im_nx = nx;
+    e->im_ny = ny;
+    e->im_nz = nz;
+    return 0;
+}
+
+static int upload_strided(s3d_engine *e, float *dev, const float *host, int nx, int ny, int nz,
+                          size_t xs, size_t ys, size_t zs)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    if (xs == 1 && ys == (size_t)nx && zs == (size_t)nx * ny) {
+        S3D_CUDA(e, cudaMemcpyAsync(dev, host, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        return 0;
+    }
+    if (xs == 1) {  // padded rows/planes: a 3-D strided copy
+        cudaMemcpy3DParms p = {};
+        p.srcPtr = make_cudaPitchedPtr((void *)host, ys * sizeof(float), nx, zs / ys);
+        p.dstPtr = make_cudaPitchedPtr(dev, (size_t)nx * sizeof(float), nx, ny);
+        p.extent = make_cudaExtent((size_t)nx * sizeof(float), ny, nz);
+        p.kind = cudaMemcpyHostToDevice;
+        if (zs % ys == 0) {
+            S3D_CUDA(e, cudaMemcpy3DAsync(&p, e->stream));
+            return 0;
+        }
+    }
+    // arbitrary element strides (im_copy_data honours them, imutil.c:1913-1916): gather first
+    std::vector<float> tmp(n);
+    for (int z = 0; z < nz; z++)
+        for (int y = 0; y < ny; y++)
+            for (int x = 0; x < nx; x++)
+                tmp[x + (size_t)nx * (y + (size_t)ny * z)] = host[x * xs + y * ys + z * zs];
+    S3D_CUDA(e, cudaMemcpyAsync(dev, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int s3d_image_upload(s3d_engine *e, const float *host, int nx, int ny, int nz, size_t xs,
+                     size_t ys, size_t zs)
+{
+    DeviceGuard guard(e->device);
+    if (ensure_im(e, nx, ny, nz)) return -1;
+    return upload_strided(e, e->im, host, nx, ny, nz, xs, ys, zs);
+}
+
+int s3d_image_from_device(s3d_engine *e, const float *dev, int nx, int ny, int nz)
+{
+    DeviceGuard guard(e->device);
+    if (ensure_im(e, nx, ny, nz)) return -1;
+    S3D_CUDA(e, cudaMemcpyAsync(e->im, dev, (size_t)nx * ny * nz * sizeof(float),
+                                cudaMemcpyDeviceToDevice, e->stream));
+    return 0;
+}
+
+int s3d_build_pyramid(s3d_engine *e)
+{
+    DeviceGuard guard(e->device);
+    if (e->noct < 1 || !e->im || (int)e->oct_taps.size() != e->nlev_g - 1)
+        return s3d_fail(e, "s3d_build_pyramid: pyramid/filters/image not configured", cudaSuccess,
+                        __FILE__, __LINE__);
+    const LevelDev &base = e->g[0];
+    if (base.g.nx != e->im_nx || base.g.ny != e->im_ny || base.g.nz != e->im_nz)
+        return s3d_fail(e, "s3d_build_pyramid: image/pyramid size mismatch", cudaSuccess, __FILE__,
+                        __LINE__);
+    const size_t n0 = base.n();
+    S3D_CUDA(e, cudaMemsetAsync(e->d_scalars, 0, e->n_scalars * sizeof(unsigned), e->stream));
+    // im_scale (imutil.c:1977-1991)
+    if (s3d_k_max_abs(e, e->im, n0, e->d_scalars)) return -1;
+    if (s3d_k_scale(e, e->im, e->im, n0, e->d_scalars)) return -1;
+    // build_gpyr (sift.c:989-1050); every hot call uses unit = 1.0 (sift.c:1002)
+    float uf[3];
+    level_uf(base.g, 1.0, uf);
+    if (s3d_k_blur(e, e->im, e->g[0].d, base.g.nx, base.g.ny, base.g.nz, 1, e->first_taps, uf))
+        return -1;
+    for (int o = 0; o < e->noct; o++) {
+        for (int s = 0; s <= e->nlev_g - 2; s++) {
+            const LevelDev &src = e->g[(size_t)o * e->nlev_g + s];  // level s-1
+            LevelDev &dst = e->g[(size_t)o * e->nlev_g + s + 1];    // level s
+            level_uf(src.g, 1.0, uf);
+            if (s3d_k_blur(e, src.d, dst.d, src.g.nx, src.g.ny, src.g.nz, 1, e->oct_taps[s], uf))
+                return -1;
+        }
+        if (o != e->noct - 1) {  // im_downsample_2x of level max(s_end-2, first) (sift.c:1029-1041)
+            const int ds = std::max(e->nlev_g - 2 - 2, -1);
+            const LevelDev &src = e->g[(size_t)o * e->nlev_g + ds + 1];
+            LevelDev &dst = e->g[(size_t)(o + 1) * e->nlev_g];
+            if (s3d_k_decimate(e, src.d, src.g.nx, src.g.ny, src.g.nz, dst.d, dst.g.nx, dst.g.ny,
+                               dst.g.nz))
+                return -1;
+        }
+    }
+    // build_dog (sift.c:1052-1071) fused with the per-level max|DoG| (sift.c:1161-1166)
+    for (int o = 0; o < e->noct; o++)
+        for (int s = -1; s <= e->nlev_d - 2; s++) {
+            const LevelDev &a = e->g[(size_t)o * e->nlev_g + s + 1];
+            const LevelDev &b = e->g[(size_t)o * e->nlev_g + s + 2];
+            LevelDev &d = e->dog[(size_t)o * e->nlev_d + s + 1];
+            if (s3d_k_dog(e, a.d, b.d, d.d, a.n(), e->d_scalars + 1 + (size_t)o * e->nlev_d + s + 1))
+                return -1;
+        }
+    return 0;
+}
+
+int s3d_detect_extrema(s3d_engine *e, double peak_thresh, int *num_candidates)
+{
+    DeviceGuard guard(e->device);
+    if (e->noct < 1)
+        return s3d_fail(e, "s3d_detect_extrema: no pyramid", cudaSuccess, __FILE__, __LINE__);
+    const size_t n0 = e->dog[0].n();
+    int want_cap = (int)std::min<size_t>(std::max<size_t>(n0 / 64, (size_t)1 << 16), (size_t)1 << 28);
+    if (e->cand_cap > want_cap) want_cap = e->cand_cap;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        if (ensure_cand(e, want_cap)) return -1;
+        S3D_CUDA(e, cudaMemsetAsync(e->d_counter, 0, 4 * sizeof(int), e->stream));
+        for (int o = 0; o < e->noct; o++)
+            if (s3d_k_extrema_octave(e, o, 0.0f, peak_thresh)) return -1;
+        int total = 0;
+        S3D_CUDA(e, cudaMemcpyAsync(&total, e->d_counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+        if (total <= e->cand_cap) {
+            e->ncand = total;
+            e->nkp = 0;
+            if (num_candidates) *num_candidates = total;
+            return 0;
+        }
+        want_cap = total + total / 8 + 1024;  // overflowed: grow and redo the (cheap) scan
+    }
+    return s3d_fail(e, "s3d_detect_extrema: candidate buffer", cudaSuccess, __FILE__, __LINE__);
+}
+
+int s3d_assign_orientations(s3d_engine *e, double corner_thresh, int *num_keypoints)
+{
+    DeviceGuard guard(e->device);
+    if (s3d_k_orientations(e, corner_thresh)) return -1;
+    int nkp = 0;
+    if (e->ncand > 0) {
+        S3D_CUDA(e, cudaMemcpyAsync(&nkp, e->d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
+    e->nkp = nkp;
+    if (num_keypoints) *num_keypoints = nkp;
+    return 0;
+}
+
+int s3d_keypoints_download(s3d_engine *e, s3d_keypoint *out, int cap)
+{
+    DeviceGuard guard(e->device);
+    const int n = std::min(cap, e->nkp);
+    if (n <= 0) return 0;
+    S3D_CUDA(e, cudaMemcpyAsync(out, e->d_kp, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyDeviceToHost, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int s3d_candidates_download(s3d_engine *e, s3d_keypoint *out, int cap)
+{
+    DeviceGuard guard(e->device);
+    const int n = std::min(cap, e->ncand);
+    if (n <= 0) return 0;
+    // d_kp_all holds the candidates (with R of the last orientation pass, if any)
+    if (e->nkp == 0 && s3d_pack_candidates(e, e->d_kp_all)) return -1;
+    S3D_CUDA(e, cudaMemcpyAsync(out, e->d_kp_all, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyDeviceToHost, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+const s3d_keypoint *s3d_device_keypoints(const s3d_engine *e) { return e->d_kp; }
+
+int s3d_extract_descriptors_device(s3d_engine *e, const s3d_keypoint *dev_kp, int n,
+                                   void *dev_desc)
+{
+    DeviceGuard guard(e->device);
+    if (e->noct < 1)
+        return s3d_fail(e, "s3d_extract_descriptors: no pyramid", cudaSuccess, __FILE__, __LINE__);
+    return s3d_k_descriptors(e, dev_kp, n, (unsigned char *)dev_desc);
+}
+
+int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *host_desc)
+{
+    DeviceGuard guard(e->device);
+    if (n < 1) return s3d_fail(e, "s3d_extract_descriptors: n < 1", cudaSuccess, __FILE__, __LINE__);
+    if (e->noct < 1)
+        return s3d_fail(e, "s3d_extract_descriptors: no pyramid", cudaSuccess, __FILE__, __LINE__);
+    for (int i = 0; i < n; i++)
+        if (kp[i].o < 0 || kp[i].o >= e->noct || kp[i].s < e->first_level ||
+            kp[i].s > e->first_level + e->nlev_g - 1)
+            return s3d_fail(e, "s3d_extract_descriptors: keypoint octave/level outside the pyramid",
+                            cudaSuccess, __FILE__, __LINE__);
+    if (n > e->kp_in_cap) {
+        if (e->d_kp_in) cudaFree(e->d_kp_in);
+        e->d_kp_in = nullptr;
+        e->kp_in_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->d_kp_in, (size_t)n * sizeof(s3d_keypoint)));
+        e->kp_in_cap = n;
+    }
+    const size_t bytes = (size_t)n * S3D_DESC_STRIDE;
+    if (bytes > e->desc_cap) {
+        if (e->d_desc) cudaFree(e->d_desc);
+        e->d_desc = nullptr;
+        e->desc_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->d_desc, bytes));
+        e->desc_cap = bytes;
+    }
+    S3D_CUDA(e, cudaMemcpyAsync(e->d_kp_in, kp, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyHostToDevice, e->stream));
+    if (s3d_k_descriptors(e, e->d_kp_in, n, e->d_desc)) return -1;
+    S3D_CUDA(e, cudaMemcpyAsync(host_desc, e->d_desc, bytes, cudaMemcpyDeviceToHost, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int s3d_single_level(s3d_engine *e, const float *host, int nx, int ny, int nz, size_t xs, size_t ys,
+                     size_t zs, const double units[3], double scale, const s3d_filter *smooth)
+{  // SIFT3D_extract_raw_descriptors / SIFT3D_assign_orientations: a one-level pyramid
+   // (first_octave 0, first_level 0; sift.c:2140-2165) holding smooth_scale_raw_input
+    DeviceGuard guard(e->device);
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    TapSet ts;
+    if (to_tapset(e, smooth, ts)) return -1;
+    const bool same = e->noct == 1 && e->nlev_g == 1 && e->first_level == 0 && e->g.size() == 1 &&
+                      e->g[0].g.nx == nx && e->g[0].g.ny == ny && e->g[0].g.nz == nz;
+    if (!same) {
+        free_pyramid(e);
+        e->noct = 1;
+        e->K = 1;
+        e->nlev_g = 1;
+        e->nlev_d = 0;
+        e->first_level = 0;
+        e->g.resize(1);
+        e->g[0].g.nx = nx;
+        e->g[0].g.ny = ny;
+        e->g[0].g.nz = nz;
+        S3D_CUDA(e, cudaMalloc(&e->g[0].d, (size_t)nx * ny * nz * sizeof(float)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_ptrs, sizeof(float *)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_dims, 3 * sizeof(int)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_units, 3 * sizeof(float)));
+        S3D_CUDA(e, cudaMalloc(&e->d_level_scales, sizeof(double)));
+        e->n_scalars = 1;
+        S3D_CUDA(e, cudaMalloc(&e->d_scalars, sizeof(unsigned)));
+    }
+    e->g[0].g.ux = units[0];
+    e->g[0].g.uy = units[1];
+    e->g[0].g.uz = units[2];
+    e->g[0].g.scale = scale;
+    const int dims[3] = {nx, ny, nz};
+    const float fu[3] = {(float)units[0], (float)units[1], (float)units[2]};
+    S3D_CUDA(e, cudaMemcpy(e->d_level_ptrs, &e->g[0].d, sizeof(float *), cudaMemcpyHostToDevice));
+    S3D_CUDA(e, cudaMemcpy(e->d_level_dims, dims, sizeof(dims), cudaMemcpyHostToDevice));
+    S3D_CUDA(e, cudaMemcpy(e->d_level_units, fu, sizeof(fu), cudaMemcpyHostToDevice));
+    S3D_CUDA(e, cudaMemcpy(e->d_level_scales, &scale, sizeof(double), cudaMemcpyHostToDevice));
+    if (ensure_im(e, nx, ny, nz)) return -1;
+    if (upload_strided(e, e->im, host, nx, ny, nz, xs, ys, zs)) return -1;
+    const float uf[3] = {(float)(1.0 / units[0]), (float)(1.0 / units[1]), (float)(1.0 / units[2])};
+    if (s3d_k_blur(e, e->im, e->g[0].d, nx, ny, nz, 1, ts, uf)) return -1;
+    const size_t n = (size_t)nx * ny * nz;
+    if (s3d_k_max_abs(e, e->g[0].d, n, e->d_scalars)) return -1;
+    if (s3d_k_scale(e, e->g[0].d, e->g[0].d, n, e->d_scalars)) return -1;
+    return 0;
+}
+
+int s3d_orient_keypoints(s3d_engine *e, s3d_keypoint *kp, int n, double sig_fctr,
+                         double corner_thresh, double *conf, unsigned char *ok)
+{
+    DeviceGuard guard(e->device);
+    if (n < 1 || e->noct < 1)
+        return s3d_fail(e, "s3d_orient_keypoints: no keypoints / pyramid", cudaSuccess, __FILE__, __LINE__);
+    s3d_keypoint *d_kp = nullptr;
+    double *d_conf = nullptr;
+    unsigned char *d_ok = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&d_kp, (size_t)n * sizeof(s3d_keypoint)) != cudaSuccess ||
+            cudaMalloc(&d_conf, (size_t)n * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&d_ok, (size_t)n) != cudaSuccess) {
+            s3d_fail(e, "s3d_orient_keypoints: cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
+            break;
+        }
+        cudaError_t ce = cudaMemcpyAsync(d_kp, kp, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyHostToDevice, e->stream);
+        if (ce != cudaSuccess) { s3d_fail(e, "upload", ce, __FILE__, __LINE__); break; }
+        if (s3d_k_orient_list(e, d_kp, n, sig_fctr, corner_thresh, d_ok, d_conf)) break;
+        ce = cudaMemcpyAsync(kp, d_kp, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess && conf)
+            ce = cudaMemcpyAsync(conf, d_conf, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess && ok)
+            ce = cudaMemcpyAsync(ok, d_ok, (size_t)n, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) { s3d_fail(e, "download", ce, __FILE__, __LINE__); break; }
+        rc = 0;
+    } while (0);
+    cudaStreamSynchronize(e->stream);
+    if (d_kp) cudaFree(d_kp);
+    if (d_conf) cudaFree(d_conf);
+    if (d_ok) cudaFree(d_ok);
+    return rc;
+}
+
+int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx, int ny, int nz,
+                    int nc, const float *taps, int width, double unit, const double units[3])
+{
+    DeviceGuard guard(e->device);
+    s3d_filter f = {taps, width};
+    TapSet t;
+    if (to_tapset(e, &f, t)) return -1;
+    const float uf[3] = {(float)(unit / units[0]), (float)(unit / units[1]), (float)(unit / units[2])};
+    return s3d_k_blur(e, dev_src, dev_dst, nx, ny, nz, nc, t, uf);
+}
+
+int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, int nz, size_t xs,
+                          size_t ys, size_t zs, const double units[3],
+                          const double desc_units[3], const s3d_filter *smooth,
+                          const s3d_filter *window, float *host_out)
+{
+    DeviceGuard guard(e->device);
+    const size_t n = (size_t)nx * ny * nz;
+    TapSet ts, tw;
+    if (to_tapset(e, smooth, ts) || to_tapset(e, window, tw)) return -1;
+    float *raw = nullptr, *sm = nullptr, *t12 = nullptr, *d12 = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&raw, n * 4) != cudaSuccess || cudaMalloc(&sm, n * 4) != cudaSuccess ||
+            cudaMalloc(&t12, n * 48) != cudaSuccess || cudaMalloc(&d12, n * 48) != cudaSuccess) {
+            s3d_fail(e, "dense: cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
+            break;
+        }
+        if (upload_strided(e, raw, host_in, nx, ny, nz, xs, ys, zs)) break;
+        // smooth_scale_raw_input (sift.c:1978-2006)
+        const float uf[3] = {(float)(1.0 / units[0]), (float)(1.0 / units[1]), (float)(1.0 / units[2])};
+        if (s3d_k_blur(e, raw, sm, nx, ny, nz, 1, ts, uf)) break;
+        unsigned *mx = e->d_counter ? reinterpret_cast<unsigned *>(e->d_counter + 2) : nullptr;
+        if (s3d_k_max_abs(e, sm, n, mx)) break;
+        if (s3d_k_scale(e, sm, sm, n, mx)) break;
+        // gradient direction -> barycentric channel image (sift.c:2462-2480)
+        const float fu[3] = {(float)units[0], (float)units[1], (float)units[2]};
+        const float iu[3] = {1.0f / fu[0], 1.0f / fu[1], 1.0f / fu[2]};
+        if (s3d_k_dense(e, sm, raw, nx, ny, nz, iu, t12)) break;
+        // 12-channel window blur in the units of the caller's desc image (sift.c:2451, 2483)
+        const float ufd[3] = {(float)(1.0 / desc_units[0]), (float)(1.0 / desc_units[1]),
+                              (float)(1.0 / desc_units[2])};
+        if (s3d_k_blur(e, t12, d12, nx, ny, nz, 12, tw, ufd)) break;
+        if (s3d_k_dense_post(e, d12, raw, n)) break;
+        cudaError_t ce = cudaMemcpyAsync(host_out, d12, n * 48, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) {
+            s3d_fail(e, "dense: download", ce, __FILE__, __LINE__);
+            break;
+        }
+        rc = 0;
+    } while (0);
+    cudaStreamSynchronize(e->stream);
+    if (raw) cudaFree(raw);
+    if (sm) cudaFree(sm);
+    if (t12) cudaFree(t12);
+    if (d12) cudaFree(d12);
+    return rc;
+}
+
+int s3d_level_download(s3d_engine *e, int which, int o, int s, float *host_dst)
+{
+    DeviceGuard guard(e->device);
+    const int nl = which ? e->nlev_d : e->nlev_g;
+    if (o < 0 || o >= e->noct || s < -1 || s > nl - 2)
+        return s3d_fail(e, "s3d_level_download: index", cudaSuccess, __FILE__, __LINE__);
+    const LevelDev &l = which ? e->dog[(size_t)o * nl + s + 1] : e->g[(size_t)o * nl + s + 1];
+    S3D_CUDA(e, cudaMemcpyAsync(host_dst, l.d, l.n() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int s3d_pyramid_copy(s3d_engine *dst, const s3d_engine *src)
+{
+    if (src->noct == 0) return 0;
+    std::vector<s3d_geom> g(src->g.size()), d(src->dog.size());
+    for (size_t i = 0; i < g.size(); i++) g[i] = src->g[i].g;
+    for (size_t i = 0; i < d.size(); i++) d[i] = src->dog[i].g;
+    if (s3d_pyramid_resize(dst, src->noct, src->K, g.data(), d.data())) return -1;
+    DeviceGuard guard(dst->device);
+    cudaStreamSynchronize(src->stream);
+    for (size_t i = 0; i < g.size(); i++)
+        S3D_CUDA(dst, cudaMemcpyPeerAsync(dst->g[i].d, dst->device, src->g[i].d, src->device,
+                                          src->g[i].n() * sizeof(float), dst->stream));
+    for (size_t i = 0; i < d.size(); i++)
+        S3D_CUDA(dst, cudaMemcpyPeerAsync(dst->dog[i].d, dst->device, src->dog[i].d, src->device,
+                                          src->dog[i].n() * sizeof(float), dst->stream));
+    dst->first_taps = src->first_taps;
+    dst->oct_taps = src->oct_taps;
+    S3D_CUDA(dst, cudaStreamSynchronize(dst->stream));
+    return 0;
+}
+
+void *s3d_dev_alloc(s3d_engine *e, size_t bytes)
+{
+    DeviceGuard guard(e->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        s3d_fail(e, "s3d_dev_alloc", cudaGetLastError(), __FILE__, __LINE__);
+        return nullptr;
+    }
+    return p;
+}
+
+void s3d_dev_free(s3d_engine *e, void *p)
+{
+    DeviceGuard guard(e->device);
+    if (p) cudaFree(p);
+}
+
+int s3d_memcpy_h2d(s3d_engine *e, void *dev, const void *host, size_t bytes)
+{
+    DeviceGuard guard(e->device);
+    S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int s3d_memcpy_d2h(s3d_engine *e, void *host, const void *dev, size_t bytes)
+{
+    DeviceGuard guard(e->device);
+    S3D_CUDA(e, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+}  // extern "C"

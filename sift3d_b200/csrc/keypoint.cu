@@ -1,0 +1,703 @@
+// keypoint.cu -- orientation assignment, sparse descriptors and dense descriptors.
+//
+// Replaces (reference bbrister/SIFT3D v1.4.6):
+//   assign_orientations / assign_eig_ori   sift.c:1264-1514  (+ eigen_Mat_rm imutil.c:2992)
+//   extract_descrip / SIFT3D_desc_acc_interp / icos_hist_bin / cart2bary / normalize_desc
+//                                           sift.c:1834-1928, 1687-1791, 1646-1683, 335-394, 1794-1821
+//   extract_dense_descriptors_no_rotate / postproc_Hist   sift.c:2429-2496, 2246-2292
+//
+// Precision rule: all geometry is evaluated in f32 in the
+// reference's operation order with separately rounded multiplies and adds; only
+// the ORDER of histogram accumulation differs (parallel), which costs ~1e-7
+// relative L2 against a 1e-4 budget.
+#include "common.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+// a*b + c*d + e*f in the reference's left-to-right order
+__device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f)
+{
+    return fa(fa(fm(a, b), fm(c, d)), fm(e, f));
+}
+
+#define K_BARY_EPS ((double)FLT_EPSILON * 1E1)
+
+// cart2bary (sift.c:335-394) with the per-face constants hoisted.
+__device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], float bary[3])
+{
+    float p[3];
+    p[0] = fs(fm(g[1], F.e2[2]), fm(g[2], F.e2[1]));
+    p[1] = fs(fm(g[2], F.e2[0]), fm(g[0], F.e2[2]));
+    p[2] = fs(fm(g[0], F.e2[1]), fm(g[1], F.e2[0]));
+    const float det = dot3(F.e1[0], p[0], F.e1[1], p[1], F.e1[2], p[2]);
+    if ((double)fabsf(det) < K_BARY_EPS) return false;
+    const float det_inv = __fdiv_rn(1.0f, det);
+    bary[1] = fm(det_inv, dot3(F.t[0], p[0], F.t[1], p[1], F.t[2], p[2]));
+    bary[2] = fm(det_inv, dot3(g[0], F.q[0], g[1], F.q[1], g[2], F.q[2]));
+    bary[0] = fs(fs(1.0f, bary[1]), bary[2]);
+    const float k = fm(F.e2q, det_inv);
+    return !((double)bary[0] < -K_BARY_EPS || (double)bary[1] < -K_BARY_EPS ||
+             (double)bary[2] < -K_BARY_EPS || k < 0.0f);
+}
+
+// icos_hist_bin (sift.c:1646-1683): FIRST face in table order that passes.
+// Fast path: the face whose three vertices have the largest dot products with g
+// is the containing face; if its barycentrics are all comfortably positive no
+// other face can pass (faces only overlap within bary_eps of shared edges), so
+// it is also the first.  Otherwise fall back to the literal in-order loop.
+__device__ __forceinline__ int icos_bin(const MeshDev *__restrict__ M, const float g[3],
+                                        float bary[3])
+{
+    const float n2 = fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2]));
+    if ((double)n2 < K_BARY_EPS) return -1;
+    // preselect by centroid direction (any monotone proxy is fine: it is verified)
+    int best = 0;
+    float bd = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < 20; i++) {
+        const float d = g[0] * M->f[i].vmid[0] + g[1] * M->f[i].vmid[1] + g[2] * M->f[i].vmid[2];
+        if (d > bd) {
+            bd = d;
+            best = i;
+        }
+    }
+    const float margin = 1e-4f;
+    if (face_test(M->f[best], g, bary) && bary[0] > margin && bary[1] > margin &&
+        bary[2] > margin)
+        return best;
+    for (int i = 0; i < 20; i++)
+        if (face_test(M->f[i], g, bary)) return i;
+    return -1;
+}
+
+// cyclic Jacobi, f64, ascending eigenvalues, eigenvectors in the columns of Q
+// (stand-in for LAPACK dsyevd, imutil.c:2992-3075; same algorithm as the oracle
+// port so the two agree bit for bit)
+__device__ void eig3(const double Ain[9], double Q[9], double L[3])
+{
+    double A[3][3], V[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            A[i][j] = Ain[3 * i + j];
+            V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 64; sweep++) {
+        const double off = __dadd_rn(__dadd_rn(fabs(A[0][1]), fabs(A[0][2])), fabs(A[1][2]));
+        if (off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = p + 1; q < 3; q++) {
+                if (A[p][q] == 0.0) continue;
+                const double theta =
+                    __ddiv_rn(__dsub_rn(A[q][q], A[p][p]), __dmul_rn(2.0, A[p][q]));
+                const double t = __ddiv_rn(
+                    theta >= 0 ? 1.0 : -1.0,
+                    __dadd_rn(fabs(theta), __dsqrt_rn(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
+                const double cs = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(t, t), 1.0)));
+                const double sn = __dmul_rn(t, cs);
+                const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
+                A[p][p] = __dsub_rn(app, __dmul_rn(t, apq));
+                A[q][q] = __dadd_rn(aqq, __dmul_rn(t, apq));
+                A[p][q] = A[q][p] = 0.0;
+                const int r = 3 - p - q;
+                {
+                    const double arp = A[r][p], arq = A[r][q];
+                    A[r][p] = A[p][r] = __dsub_rn(__dmul_rn(cs, arp), __dmul_rn(sn, arq));
+                    A[r][q] = A[q][r] = __dadd_rn(__dmul_rn(sn, arp), __dmul_rn(cs, arq));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const double vrp = V[k][p], vrq = V[k][q];
+                    V[k][p] = __dsub_rn(__dmul_rn(cs, vrp), __dmul_rn(sn, vrq));
+                    V[k][q] = __dadd_rn(__dmul_rn(sn, vrp), __dmul_rn(cs, vrq));
+                }
+            }
+    }
+    int order[3] = {0, 1, 2};
+    double dg[3] = {A[0][0], A[1][1], A[2][2]};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i + 1; j < 3; j++)
+            if (dg[order[j]] < dg[order[i]]) {
+                const int t = order[i];
+                order[i] = order[j];
+                order[j] = t;
+            }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        L[i] = dg[order[i]];
+#pragma unroll
+        for (int j = 0; j < 3; j++) Q[3 * j + i] = V[j][order[i]];
+    }
+}
+
+struct PyrTable {
+    float *const *ptrs;  // gpyr level pointers [o*nlev_g + s+1]
+    const int *dims;     // 3 per level
+    const float *units;  // 3 per level ((float) ux, uy, uz)
+    const double *scales;
+    int nlev_g;
+    int first_level;
+};
+
+// IM_LOOP_SPHERE_START bounds (sift.c:96-119) with a double radius
+__device__ __forceinline__ void sphere_bounds_d(float c, double rad, float uf, int n, int &lo,
+                                                int &hi)
+{
+    lo = (int)fmaxf(floorf((float)((double)c - rad / (double)uf)), 1.0f);
+    hi = (int)fminf(ceilf((float)((double)c + rad / (double)uf)), (float)(n - 2));
+}
+// ... and with a float radius
+__device__ __forceinline__ void sphere_bounds_f(float c, float rad, float uf, int n, int &lo,
+                                                int &hi)
+{
+    lo = (int)fmaxf(floorf(fs(c, __fdiv_rn(rad, uf))), 1.0f);
+    hi = (int)fminf(ceilf(fa(c, __fdiv_rn(rad, uf))), (float)(n - 2));
+}
+
+// ---------------------------------------------------------------- orientation
+// One thread per candidate, accumulating in the reference's raster order so the
+// f32 window gradient and the f64 structure tensor see the same rounding
+// sequence as the CPU (SURVEY.md "Orientation accept/reject flips").  Candidates
+// adjacent in scan order share (o, s) and integer centres, so the lanes of a warp
+// walk identical offsets in lock step.
+__global__ void __launch_bounds__(128)
+    k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
+             double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const s3d_keypoint c = kps[i];
+    const int lv = c.o * T.nlev_g + (c.s - T.first_level);
+    const float *__restrict__ im = T.ptrs[lv];
+    const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
+    const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
+    const float vcx = c.x, vcy = c.y, vcz = c.z;
+    // detector: sigma = ori_sig_fctr * key->sd (sift.c:1281); raw API: sigma = key_base.sd
+    // (sift.c:1579)
+    const double sigma = sig_fctr * c.sd;
+    const double win_radius = sigma * 3.0;  // ori_rad_fctr, sift.c:1365
+    const double r2 = win_radius * win_radius;
+    const double s2 = sigma * sigma;
+    const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
+    int x0, x1, y0, y1, z0, z1;
+    sphere_bounds_d(vcx, win_radius, uxf, nx, x0, x1);
+    sphere_bounds_d(vcy, win_radius, uyf, ny, y0, y1);
+    sphere_bounds_d(vcz, win_radius, uzf, nz, z0, z1);
+    const size_t ys = nx, zs = (size_t)nx * ny;
+
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    float wx = 0.0f, wy = 0.0f, wz = 0.0f;
+    for (int z = z0; z <= z1; z++) {
+        const float dz = fm(fs((float)z, vcz), uzf);
+        const float dz2 = fm(dz, dz);
+        for (int y = y0; y <= y1; y++) {
+            const float dy = fm(fs((float)y, vcy), uyf);
+            const float dy2 = fm(dy, dy);
+            const float *row = im + (size_t)y * ys + (size_t)z * zs;
+            for (int x = x0; x <= x1; x++) {
+                const float dx = fm(fs((float)x, vcx), uxf);
+                const float sq = fa(fa(fm(dx, dx), dy2), dz2);
+                if ((double)sq > r2) continue;
+                // weight = expf(-0.5 * sq_dist / (sigma * sigma)), sift.c:1401: f64
+                // argument narrowed to f32, then a correctly rounded f32 exp
+                const float arg = (float)__ddiv_rn(__dmul_rn(-0.5, (double)sq), s2);
+                const float w = (float)exp((double)arg);
+                const float *p = row + x;
+                float gx = fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1)));
+                float gy = fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys)));
+                float gz = fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs)));
+                gx = fm(gx, iux);
+                gy = fm(gy, iuy);
+                gz = fm(gz, iuz);
+                const double dw = (double)w, gxd = gx, gyd = gy, gzd = gz;
+                a00 = __dadd_rn(a00, __dmul_rn(__dmul_rn(gxd, gxd), dw));
+                a01 = __dadd_rn(a01, __dmul_rn(__dmul_rn(gxd, gyd), dw));
+                a02 = __dadd_rn(a02, __dmul_rn(__dmul_rn(gxd, gzd), dw));
+                a11 = __dadd_rn(a11, __dmul_rn(__dmul_rn(gyd, gyd), dw));
+                a12 = __dadd_rn(a12, __dmul_rn(__dmul_rn(gyd, gzd), dw));
+                a22 = __dadd_rn(a22, __dmul_rn(__dmul_rn(gzd, gzd), dw));
+                wx = fa(wx, fm(gx, w));
+                wy = fa(wy, fm(gy, w));
+                wz = fa(wz, fm(gz, w));
+            }
+        }
+    }
+    bool accept = true;
+    double conf = 0.0;
+    float R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const float wn2 = fa(fa(fm(wx, wx), fm(wy, wy)), fm(wz, wz));
+    if (wn2 < (float)1E-10) accept = false;  // ori_grad_thresh, sift.c:1426
+    if (accept) {
+        const double A[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
+        double Q[9], L[3];
+        eig3(A, Q, L);
+        if (fabs(__ddiv_rn(L[0], L[1])) > 0.90 || fabs(__ddiv_rn(L[1], L[2])) > 0.90)
+            accept = false;  // max_eig_ratio, sift.c:1440-1444
+        if (accept) {
+            double corner = DBL_MAX;
+            float v[2][3];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {  // sift.c:1448-1480
+                const int ei = 2 - k;
+                float vr0 = (float)Q[0 * 3 + ei], vr1 = (float)Q[1 * 3 + ei],
+                      vr2 = (float)Q[2 * 3 + ei];
+                const double d = (double)dot3(wx, vr0, wy, vr1, wz, vr2);
+                const float nv = __fsqrt_rn(fa(fa(fm(vr0, vr0), fm(vr1, vr1)), fm(vr2, vr2)));
+                const float nw = __fsqrt_rn(wn2);
+                const double cos_ang = __ddiv_rn(d, (double)fm(nv, nw));
+                corner = fmin(corner, fabs(cos_ang));
+                const float sgn = d > 0.0 ? 1.0f : -1.0f;
+                vr0 = fm(vr0, sgn);
+                vr1 = fm(vr1, sgn);
+                vr2 = fm(vr2, sgn);
+                R[0 * 3 + k] = vr0;
+                R[1 * 3 + k] = vr1;
+                R[2 * 3 + k] = vr2;
+                v[k][0] = vr0;
+                v[k][1] = vr1;
+                v[k][2] = vr2;
+            }
+            R[0 * 3 + 2] = fs(fm(v[0][1], v[1][2]), fm(v[0][2], v[1][1]));
+            R[1 * 3 + 2] = fs(fm(v[0][2], v[1][0]), fm(v[0][0], v[1][2]));
+            R[2 * 3 + 2] = fs(fm(v[0][0], v[1][1]), fm(v[0][1], v[1][0]));
+            conf = corner;
+            if (corner < corner_thresh) accept = false;  // sift.c:1340-1341
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) kps[i].R[k] = R[k];
+    ok[i] = accept ? 1 : 0;
+    if (conf_out) conf_out[i] = conf;
+}
+
+// ordered compaction of accepted candidates (sift.c:1306-1324)
+__global__ void __launch_bounds__(1024)
+    k_flag_scan(const unsigned char *__restrict__ ok, int n, int *__restrict__ pos,
+                int *__restrict__ counter)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? ok[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += t;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+        const int run = s_run;
+        if (i < n) pos[i] = run + warp_off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = run + warp_off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counter[1] = s_run;
+}
+
+__global__ void __launch_bounds__(256)
+    k_cand_to_keypoints(const Candidate *__restrict__ cand, int n, const double *__restrict__ scales,
+                        int nlev_g, int first_level, s3d_keypoint *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Candidate c = cand[i];
+    s3d_keypoint k;
+#pragma unroll
+    for (int j = 0; j < 9; j++) k.R[j] = 0.0f;
+    k.x = (float)c.x;  // key->xd = (double) x (sift.c:1203) -> Cvec float (sift.c:1280)
+    k.y = (float)c.y;
+    k.z = (float)c.z;
+    k.sd = scales[c.o * nlev_g + (c.s - first_level)];  // key->sd = cur->s (sift.c:1202)
+    k.o = c.o;
+    k.s = c.s;
+    out[i] = k;
+}
+
+__global__ void __launch_bounds__(256)
+    k_compact_keypoints(const s3d_keypoint *__restrict__ in, const unsigned char *__restrict__ ok,
+                        const int *__restrict__ pos, int n, s3d_keypoint *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !ok[i]) return;
+    out[pos[i]] = in[i];
+}
+
+// ---------------------------------------------------------------- sparse descriptor
+// One CTA per keypoint; the threads sweep the bounding box of the window sphere.
+#define DESC_THREADS 256
+
+__global__ void __launch_bounds__(DESC_THREADS)
+    k_descriptor(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
+                 const MeshDev *__restrict__ M, unsigned char *__restrict__ out)
+{
+    __shared__ float hist[S3D_DESC_NUMEL];
+    __shared__ double s_red[DESC_THREADS / 32];
+    __shared__ float s_norm_inv;
+    const int ki = blockIdx.x;
+    if (ki >= n) return;
+    const s3d_keypoint kp = kps[ki];
+    const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
+    const float *__restrict__ im = T.ptrs[lv];
+    const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
+    const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
+    const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
+    // sift.c:1845-1850
+    const float sigma = (float)__dmul_rn(kp.sd, 7.071067812);
+    const float win_radius = (float)__dmul_rn(2.0, (double)sigma);
+    const float half = (float)__ddiv_rn((double)win_radius, sqrt(2.0));
+    const float desc_width = fm(2.0f, half);
+    const float hist_width = __fdiv_rn(desc_width, 4.0f);
+    const float bin_fctr = __fdiv_rn(1.0f, hist_width);
+    const float r2 = fm(win_radius, win_radius);
+    const float s2 = fm(sigma, sigma);
+    int x0, x1, y0, y1, z0, z1;
+    sphere_bounds_f(kp.x, win_radius, uxf, nx, x0, x1);
+    sphere_bounds_f(kp.y, win_radius, uyf, ny, y0, y1);
+    sphere_bounds_f(kp.z, win_radius, uzf, nz, z0, z1);
+    // Rt = R^T (sift.c:1854-1857)
+    float Rt[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Rt[3 * i + j] = kp.R[3 * j + i];
+
+    for (int i = threadIdx.x; i < S3D_DESC_NUMEL; i += DESC_THREADS) hist[i] = 0.0f;
+    __syncthreads();
+
+    const int bx = max(x1 - x0 + 1, 0), by = max(y1 - y0 + 1, 0), bz = max(z1 - z0 + 1, 0);
+    const int vol = bx * by * bz;
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    for (int t = threadIdx.x; t < vol; t += DESC_THREADS) {
+        const int x = x0 + t % bx;
+        const int r = t / bx;
+        const int y = y0 + r % by;
+        const int z = z0 + r / by;
+        const float vx = fm(fs((float)x, kp.x), uxf);
+        const float vy = fm(fs((float)y, kp.y), uyf);
+        const float vz = fm(fs((float)z, kp.z), uzf);
+        const float sq = fa(fa(fm(vx, vx), fm(vy, vy)), fm(vz, vz));
+        if (sq > r2) continue;
+        float vb[3];
+        bool inside = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float vk = dot3(Rt[3 * a], vx, Rt[3 * a + 1], vy, Rt[3 * a + 2], vz);
+            vb[a] = fm(fa(vk, half), bin_fctr);
+            inside = inside && !(vb[a] < 0.0f || vb[a] >= 4.0f);
+        }
+        if (!inside) continue;
+        const float *p = im + x + (size_t)y * ys + (size_t)z * zs;
+        float g[3];
+        g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+        g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+        g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+        const float w = expf(__fdiv_rn(fm(-0.5f, sq), s2));  // sift.c:1890 (f32 throughout)
+        g[0] = fm(g[0], w);
+        g[1] = fm(g[1], w);
+        g[2] = fm(g[2], w);
+        float gr[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
+        float bary[3];
+        const int bin = icos_bin(M, gr, bary);
+        if (bin < 0) continue;
+        const float mag = __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
+        float dv[3];
+        int ib[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            dv[a] = fs(vb[a], floorf(vb[a]));
+            ib[a] = (int)vb[a];
+        }
+        const int i0 = M->f[bin].idx[0], i1 = M->f[bin].idx[1], i2 = M->f[bin].idx[2];
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                for (int dz = 0; dz < 2; dz++) {
+                    const int cx = ib[0] + dx, cy = ib[1] + dy, cz = ib[2] + dz;
+                    if (cx >= 4 || cy >= 4 || cz >= 4) continue;  // lower bounds hold (vb >= 0)
+                    const float wgt = fm(fm(dx ? dv[0] : fs(1.0f, dv[0]), dy ? dv[1] : fs(1.0f, dv[1])),
+                                         dz ? dv[2] : fs(1.0f, dv[2]));
+                    float *h = hist + 12 * (cx + 4 * cy + 16 * cz);
+                    const float mw = fm(mag, wgt);
+                    atomicAdd(h + i0, fm(mw, bary[0]));
+                    atomicAdd(h + i1, fm(mw, bary[1]));
+                    atomicAdd(h + i2, fm(mw, bary[2]));
+                }
+    }
+    __syncthreads();
+
+    // normalize_desc (sift.c:1794-1821), truncate (sift.c:1909-1915), normalize again
+    const float trunc = (float)((double)(0.2f * 128.0f / S3D_DESC_NUMEL));
+    for (int pass = 0; pass < 2; pass++) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < S3D_DESC_NUMEL; i += DESC_THREADS) {
+            const double v = (double)hist[i];
+            acc = __dadd_rn(acc, __dmul_rn(v, v));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < DESC_THREADS / 32; i++) tot += s_red[i];
+            const double norm = sqrt(tot) + DBL_EPSILON;
+            s_norm_inv = (float)(1.0 / norm);
+        }
+        __syncthreads();
+        const float ninv = s_norm_inv;
+        for (int i = threadIdx.x; i < S3D_DESC_NUMEL; i += DESC_THREADS) {
+            float v = fm(hist[i], ninv);
+            if (pass == 0) v = fminf(v, trunc);
+            hist[i] = v;
+        }
+        __syncthreads();
+    }
+    float *o32 = reinterpret_cast<float *>(out + (size_t)ki * S3D_DESC_STRIDE);
+    for (int i = threadIdx.x; i < S3D_DESC_NUMEL; i += DESC_THREADS) o32[i] = hist[i];
+    if (threadIdx.x == 0) {
+        double *o64 = reinterpret_cast<double *>(out + (size_t)ki * S3D_DESC_STRIDE +
+                                                 S3D_DESC_NUMEL * sizeof(float));
+        const double f = ldexp(1.0, kp.o);  // sift.c:1851, 1922-1925
+        o64[0] = (double)kp.x * f;
+        o64[1] = (double)kp.y * f;
+        o64[2] = (double)kp.z * f;
+        o64[3] = kp.sd;
+    }
+}
+
+// ---------------------------------------------------------------- dense descriptors
+// extract_dense_descriptors_no_rotate (sift.c:2462-2480): barycentric weights of
+// the gradient direction, written to three of the twelve channels.
+__global__ void __launch_bounds__(256)
+    k_dense_bary(const float *__restrict__ sm, int nx, int ny, int nz, float iux, float iuy,
+                 float iuz, const MeshDev *__restrict__ M, float *__restrict__ temp)
+{
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % nx);
+        const size_t r = idx / nx;
+        const int y = (int)(r % ny);
+        const int z = (int)(r / ny);
+        float h[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) h[k] = 0.0f;
+        if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
+            const float *p = sm + idx;
+            float g[3], bary[3];
+            g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+            g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+            g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+            const int bin = icos_bin(M, g, bary);
+            if (bin >= 0) {
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    if (k == M->f[bin].idx[0]) h[k] = bary[0];
+                    if (k == M->f[bin].idx[1]) h[k] = bary[1];
+                    if (k == M->f[bin].idx[2]) h[k] = bary[2];
+                }
+            }
+        }
+        float4 *o = reinterpret_cast<float4 *>(temp + idx * 12);
+        o[0] = make_float4(h[0], h[1], h[2], h[3]);
+        o[1] = make_float4(h[4], h[5], h[6], h[7]);
+        o[2] = make_float4(h[8], h[9], h[10], h[11]);
+    }
+}
+
+// postproc_Hist (sift.c:2267-2292): normalise, clamp, normalise, x intensity
+__global__ void __launch_bounds__(256)
+    k_dense_post(float *__restrict__ desc, const float *__restrict__ raw, size_t nvox)
+{
+    const float hist_trunc = (float)((double)(0.2f * 128.0f / S3D_DESC_NUMEL) * S3D_DESC_NUMEL / 12);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nvox;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        float4 *p = reinterpret_cast<float4 *>(desc + idx * 12);
+        float4 a = p[0], b = p[1], c = p[2];
+        float h[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            double nrm = 0.0;
+#pragma unroll
+            for (int k = 0; k < 12; k++) nrm = __dadd_rn(nrm, __dmul_rn((double)h[k], (double)h[k]));
+            nrm = sqrt(nrm) + DBL_EPSILON;
+            const float ninv = (float)(1.0 / nrm);
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                h[k] = fm(h[k], ninv);
+                if (pass == 0) h[k] = fminf(h[k], hist_trunc);
+            }
+        }
+        const float val = __ldg(raw + idx);
+#pragma unroll
+        for (int k = 0; k < 12; k++) h[k] = fm(h[k], val);
+        p[0] = make_float4(h[0], h[1], h[2], h[3]);
+        p[1] = make_float4(h[4], h[5], h[6], h[7]);
+        p[2] = make_float4(h[8], h[9], h[10], h[11]);
+    }
+}
+
+PyrTable make_table(const s3d_engine *e)
+{
+    PyrTable T;
+    T.ptrs = e->d_level_ptrs;
+    T.dims = e->d_level_dims;
+    T.units = e->d_level_units;
+    T.scales = e->d_level_scales;
+    T.nlev_g = e->nlev_g;
+    T.first_level = e->first_level;
+    return T;
+}
+
+}  // namespace
+
+int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx)
+{
+    // per-face constants in the reference's f32 order (cart2bary, sift.c:343-364)
+    MeshDev M;
+    for (int i = 0; i < 20; i++) {
+        const float *v0 = v + 9 * i, *v1 = v0 + 3, *v2 = v0 + 6;
+        FaceConst &F = M.f[i];
+        for (int j = 0; j < 3; j++) {
+            volatile float e1 = v1[j] - v0[j];
+            volatile float e2 = v2[j] - v0[j];
+            volatile float t = v0[j] * -1.0f;
+            F.e1[j] = e1;
+            F.e2[j] = e2;
+            F.t[j] = t;
+            F.idx[j] = idx[3 * i + j];
+        }
+        {
+            volatile float a, b;
+            a = F.t[1] * F.e1[2];
+            b = F.t[2] * F.e1[1];
+            F.q[0] = a - b;
+            a = F.t[2] * F.e1[0];
+            b = F.t[0] * F.e1[2];
+            F.q[1] = a - b;
+            a = F.t[0] * F.e1[1];
+            b = F.t[1] * F.e1[0];
+            F.q[2] = a - b;
+            volatile float s0 = F.e2[0] * F.q[0], s1 = F.e2[1] * F.q[1], s2 = F.e2[2] * F.q[2];
+            volatile float s01 = s0 + s1;
+            F.e2q = s01 + s2;
+        }
+        double c[3] = {0, 0, 0}, nrm = 0;
+        for (int j = 0; j < 3; j++) c[j] = ((double)v0[j] + v1[j] + v2[j]) / 3.0;
+        for (int j = 0; j < 3; j++) nrm += c[j] * c[j];
+        nrm = sqrt(nrm);
+        for (int j = 0; j < 3; j++) F.vmid[j] = (float)(c[j] / nrm);
+    }
+    for (int i = 0; i < 12; i++)
+        for (int j = 0; j < 3; j++) M.vert[i][j] = 0.0f;
+    if (!e->d_mesh) S3D_CUDA(e, cudaMalloc(&e->d_mesh, sizeof(MeshDev)));
+    S3D_CUDA(e, cudaMemcpyAsync(e->d_mesh, &M, sizeof(M), cudaMemcpyHostToDevice, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->have_mesh = true;
+    return 0;
+}
+
+int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
+                      double corner_thresh, unsigned char *d_ok, double *d_conf)
+{
+    if (n <= 0) return 0;
+    const PyrTable T = make_table(e);
+    k_orient<<<(n + 127) / 128, 128, 0, e->stream>>>(d_kp, n, T, sig_fctr, corner_thresh, d_ok,
+                                                    d_conf);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_pack_candidates(s3d_engine *e, s3d_keypoint *d_out)
+{
+    const int n = e->ncand;
+    if (n <= 0) return 0;
+    const PyrTable T = make_table(e);
+    k_cand_to_keypoints<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_cand, n, T.scales, e->nlev_g,
+                                                               e->first_level, d_out);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_orientations(s3d_engine *e, double corner_thresh)
+{
+    const int n = e->ncand;
+    if (n <= 0) {
+        e->nkp = 0;
+        return 0;
+    }
+    if (s3d_pack_candidates(e, e->d_kp_all)) return -1;
+    // ori_sig_fctr = 1.5 (sift.c:51, 1281)
+    if (s3d_k_orient_list(e, e->d_kp_all, n, 1.5, corner_thresh, e->d_ok, nullptr)) return -1;
+    k_flag_scan<<<1, 1024, 0, e->stream>>>(e->d_ok, n, e->d_pos, e->d_counter);
+    S3D_LAUNCH_CHECK(e);
+    k_compact_keypoints<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_kp_all, e->d_ok, e->d_pos, n,
+                                                               e->d_kp);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out)
+{
+    if (n <= 0) return 0;
+    if (!e->have_mesh) return s3d_fail(e, "mesh not set", cudaSuccess, __FILE__, __LINE__);
+    const PyrTable T = make_table(e);
+    k_descriptor<<<n, DESC_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_dense(s3d_engine *e, const float *d_smooth, const float *, int nx, int ny, int nz,
+                const float inv_units[3], float *d_temp12)
+{
+    if (!e->have_mesh) return s3d_fail(e, "mesh not set", cudaSuccess, __FILE__, __LINE__);
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t want = (total + 255) / 256;
+    const size_t cap = (size_t)e->num_sms * 16;
+    k_dense_bary<<<(int)(want < cap ? want : cap), 256, 0, e->stream>>>(
+        d_smooth, nx, ny, nz, inv_units[0], inv_units[1], inv_units[2], e->d_mesh, d_temp12);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_dense_post(s3d_engine *e, float *d_desc12, const float *d_raw, size_t nvox)
+{
+    const size_t want = (nvox + 255) / 256;
+    const size_t cap = (size_t)e->num_sms * 16;
+    k_dense_post<<<(int)(want < cap ? want : cap), 256, 0, e->stream>>>(d_desc12, d_raw, nvox);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}

@@ -1,0 +1,458 @@
+// pyramid.cu -- scale-space pyramid kernels for sm_100a.
+//
+// Replaces (reference bbrister/SIFT3D v1.4.6):
+//   im_max_abs / im_scale        imutil.c:1959-1991
+//   convolve_sep_gen             imutil.c:2274-2393  (via apply_Sep_FIR_filter :3459-3544)
+//   im_downsample_2x             imutil.c:1742-1768
+//   im_subtract (build_dog)      imutil.c:1997-2017, sift.c:1052-1071
+//   detect_extrema               sift.c:1074-1212
+//
+// Arithmetic contract: every tap is
+//     acc = acc (+) tap (*) ( (1-frac) (*) lo (+) frac (*) hi )
+// with one IEEE rounding per (*) and (+), taps visited d = -hw..hw.  No FMA.
+#include "common.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- max |x|
+__global__ void __launch_bounds__(256) k_max_abs(const float *__restrict__ x, size_t n,
+                                                 unsigned *__restrict__ out_bits)
+{
+    float m = 0.0f;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    for (size_t i = tid; i < n4; i += nth) {
+        const float4 v = __ldg(x4 + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) m = fmaxf(m, fabsf(x[i]));
+    m = warp_max(m);
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0f;
+        m = warp_max(m);
+        // non-negative floats order like their bit patterns
+        if (threadIdx.x == 0) atomicMax(out_bits, __float_as_uint(m));
+    }
+}
+
+// ---------------------------------------------------------------- x / max
+__global__ void __launch_bounds__(256) k_scale(const float *__restrict__ src,
+                                               float *__restrict__ dst, size_t n,
+                                               const unsigned *__restrict__ max_bits)
+{
+    const float mx = __uint_as_float(*max_bits);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    if (mx == 0.0f) {  // im_scale returns early (imutil.c:1984-1985)
+        if (src == dst) return;
+        for (size_t i = tid; i < n4; i += nth) d4[i] = s4[i];
+        for (size_t i = n4 * 4 + tid; i < n; i += nth) dst[i] = src[i];
+        return;
+    }
+    for (size_t i = tid; i < n4; i += nth) {
+        float4 v = s4[i];
+        v.x = __fdiv_rn(v.x, mx);
+        v.y = __fdiv_rn(v.y, mx);
+        v.z = __fdiv_rn(v.z, mx);
+        v.w = __fdiv_rn(v.w, mx);
+        d4[i] = v;
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) dst[i] = __fdiv_rn(src[i], mx);
+}
+
+// ---------------------------------------------------------------- generic 1-axis FIR
+// Literal restatement of convolve_sep_gen for any axis, channel count and tap
+// spacing `uf` (= unit / units[axis], not necessarily dyadic).  This is the
+// reference-semantics path: slow but exact for every input; the fused kernel in
+// blur_fused.cu is the fast path for the common case.
+__device__ __forceinline__ float samp_acc(float acc, float tap, float c, const float *line,
+                                          size_t st, int dim_end)
+{
+    int lo = __float2int_rz(c);
+    const float frac = __fsub_rn(c, (float)lo);
+    int hi = lo + 1;
+    lo = min(max(lo, 0), dim_end);  // reads the reference leaves undefined are clamped
+    hi = min(max(hi, 0), dim_end);
+    const float v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, frac), __ldg(line + (size_t)lo * st)),
+                              __fmul_rn(frac, __ldg(line + (size_t)hi * st)));
+    return __fadd_rn(acc, __fmul_rn(tap, v));
+}
+
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src,
+                                                   float *__restrict__ dst, int nx, int ny,
+                                                   int nz, int nc, const TapSet taps, float uf)
+{
+    const size_t total = (size_t)nx * ny * nz * nc;
+    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nz);
+    const size_t st = AXIS == 0 ? (size_t)nc : (AXIS == 1 ? (size_t)nc * nx : (size_t)nc * nx * ny);
+    const int hw = taps.width / 2;
+    const int dim_end = n - 1;
+    const int uhw = (int)ceilf(__fmul_rn((float)hw, uf));
+    const int start = uhw, end = n - 1 - (uhw + 1);
+    const float conv_eps = 0.1f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx / nc;
+        const int x = (int)(r % nx);
+        r /= nx;
+        const int y = (int)(r % ny);
+        const int z = (int)(r / ny);
+        const int i = AXIS == 0 ? x : (AXIS == 1 ? y : z);
+        const float *line = src + (idx - (size_t)i * st);
+        float acc = 0.0f;
+        if (i >= start && i <= end) {
+            float c = (float)i;  // carried across taps (imutil.c:2335-2350)
+            for (int d = -hw; d <= hw; d++) {
+                const float step = __fmul_rn((float)d, uf);
+                c = __fsub_rn(c, step);
+                acc = samp_acc(acc, taps.t[d + hw], c, line, st, dim_end);
+                c = __fadd_rn(c, step);
+            }
+        } else {
+            for (int d = -hw; d <= hw; d++) {
+                const float step = __fmul_rn((float)d, uf);
+                float c = __fsub_rn((float)i, step);
+                if (__float2int_rz(c) < 0)
+                    c = -c;
+                else if (__float2int_rz(c) >= dim_end)
+                    c = __fsub_rn(__fsub_rn(__fmul_rn(2.0f, (float)dim_end), c), conv_eps);
+                acc = samp_acc(acc, taps.t[d + hw], c, line, st, dim_end);
+            }
+        }
+        dst[idx] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- 2x decimation
+__global__ void __launch_bounds__(256) k_decimate(const float *__restrict__ src, int sx, int sy,
+                                                  float *__restrict__ dst, int dx, int dy, int dz)
+{
+    const size_t total = (size_t)dx * dy * dz;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % dx);
+        const size_t r = idx / dx;
+        const int y = (int)(r % dy);
+        const int z = (int)(r / dy);
+        dst[idx] = __ldg(src + (size_t)2 * x + (size_t)sx * ((size_t)2 * y + (size_t)sy * 2 * z));
+    }
+}
+
+// ---------------------------------------------------------------- DoG + max|DoG|
+__global__ void __launch_bounds__(256) k_dog(const float *__restrict__ a,
+                                             const float *__restrict__ b, float *__restrict__ d,
+                                             size_t n, unsigned *__restrict__ max_bits)
+{
+    float m = 0.0f;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    const float4 *a4 = reinterpret_cast<const float4 *>(a);
+    const float4 *b4 = reinterpret_cast<const float4 *>(b);
+    float4 *d4 = reinterpret_cast<float4 *>(d);
+    for (size_t i = tid; i < n4; i += nth) {
+        const float4 va = __ldg(a4 + i), vb = __ldg(b4 + i);
+        float4 v;
+        v.x = __fsub_rn(va.x, vb.x);
+        v.y = __fsub_rn(va.y, vb.y);
+        v.z = __fsub_rn(va.z, vb.z);
+        v.w = __fsub_rn(va.w, vb.w);
+        d4[i] = v;
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += nth) {
+        const float v = __fsub_rn(a[i], b[i]);
+        d[i] = v;
+        m = fmaxf(m, fabsf(v));
+    }
+    m = warp_max(m);
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0f;
+        m = warp_max(m);
+        if (threadIdx.x == 0) atomicMax(max_bits, __float_as_uint(m));
+    }
+}
+
+// ---------------------------------------------------------------- extrema
+// Pass A: one thread per voxel of the octave, all K keypoint levels at once.
+// Emits a bit mask (scan order = linear voxel index) and per-block counts per
+// level, so that pass C can compact in the reference's (o, s, z, y, x) order.
+#define EXT_BLOCK 1024
+#define EXT_MAX_LEVELS 16
+
+struct ExtLevels {
+    const float *dog[EXT_MAX_LEVELS + 2];  // dog[s+1], s = -1..K
+    const unsigned *maxbits;               // dogmax bits for this octave: [s+1]
+    int K;
+};
+
+__global__ void __launch_bounds__(EXT_BLOCK)
+    k_extrema_mark(const ExtLevels L, int nx, int ny, int nz, double peak_thresh,
+                   unsigned *__restrict__ mask, int *__restrict__ blockcnt, int nblocks,
+                   size_t words_per_level)
+{
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t idx = (size_t)blockIdx.x * EXT_BLOCK + threadIdx.x;
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    bool interior = false;
+    if (idx < total) {
+        const int x = (int)(idx % nx);
+        const size_t r = idx / nx;
+        const int y = (int)(r % ny);
+        const int z = (int)(r / ny);
+        interior = x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2;
+    }
+    __shared__ int s_cnt[32];
+    for (int s = 0; s < L.K; s++) {
+        bool hit = false;
+        if (interior) {
+            // thr = (float)(peak_thresh * dogmax), sift.c:1169
+            const float thr = (float)(peak_thresh * (double)__uint_as_float(L.maxbits[s + 1]));
+            const float *cur = L.dog[s + 1] + idx;
+            const float v = __ldg(cur);
+            if (v > thr || v < -thr) {
+                const float p = __ldg(L.dog[s] + idx), q = __ldg(L.dog[s + 2] + idx);
+                const float a0 = __ldg(cur + 1), a1 = __ldg(cur - 1), a2 = __ldg(cur + ys),
+                            a3 = __ldg(cur - ys), a4 = __ldg(cur - zs), a5 = __ldg(cur + zs);
+                hit = (v > p && v > a0 && v > a1 && v > a2 && v > a3 && v > a4 && v > a5 && v > q) ||
+                      (v < p && v < a0 && v < a1 && v < a2 && v < a3 && v < a4 && v < a5 && v < q);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0) {
+            mask[(size_t)s * words_per_level + (idx >> 5)] = m;
+            s_cnt[threadIdx.x >> 5] = __popc(m);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int c = s_cnt[threadIdx.x];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (threadIdx.x == 0) blockcnt[(size_t)s * nblocks + blockIdx.x] = c;
+        }
+        __syncthreads();
+    }
+}
+
+// Pass B: exclusive scan of the per-block counts, level after level, continuing
+// the running candidate total kept in counter[0].  One block.
+__global__ void __launch_bounds__(1024) k_extrema_scan(int *__restrict__ blockcnt, int nblocks,
+                                                      int K, int *__restrict__ counter)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = counter[0];
+    __syncthreads();
+    const size_t total = (size_t)K * nblocks;
+    for (size_t base = 0; base < total; base += 1024) {
+        const size_t i = base + threadIdx.x;
+        const int v = i < total ? blockcnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += t;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+        const int run = s_run;
+        if (i < total) blockcnt[i] = run + warp_off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = run + warp_off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counter[0] = s_run;
+}
+
+// Pass C: ordered scatter of the marked voxels.
+__global__ void __launch_bounds__(EXT_BLOCK)
+    k_extrema_emit(const unsigned *__restrict__ mask, const int *__restrict__ blockoff, int nblocks,
+                   size_t words_per_level, int K, int o, int nx, int ny, int nz,
+                   Candidate *__restrict__ cand, int cap)
+{
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t idx = (size_t)blockIdx.x * EXT_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_w[32];
+    for (int s = 0; s < K; s++) {
+        const size_t word = idx >> 5;
+        const unsigned m = (word * 32 < total) ? mask[(size_t)s * words_per_level + word] : 0u;
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int v = s_w[threadIdx.x];
+            int incl = v;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, k);
+                if (threadIdx.x >= k) incl += t;
+            }
+            s_w[threadIdx.x] = incl - v;
+        }
+        __syncthreads();
+        if ((m >> lane) & 1u) {
+            const int pos = blockoff[(size_t)s * nblocks + blockIdx.x] + s_w[warp] +
+                            __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) {
+                Candidate c;
+                c.o = (short)o;
+                c.s = (short)s;
+                c.x = (int)(idx % nx);
+                const size_t r = idx / nx;
+                c.y = (int)(r % ny);
+                c.z = (int)(r / ny);
+                cand[pos] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+inline int grid_for(const s3d_engine *e, size_t work_items, int block, int per_sm)
+{
+    const size_t want = (work_items + block - 1) / block;
+    const size_t cap = (size_t)e->num_sms * per_sm;
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace
+
+int s3d_k_max_abs(s3d_engine *e, const float *x, size_t n, unsigned *d_bits)
+{
+    S3D_CUDA(e, cudaMemsetAsync(d_bits, 0, sizeof(unsigned), e->stream));
+    k_max_abs<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(x, n, d_bits);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_scale(s3d_engine *e, const float *src, float *dst, size_t n, const unsigned *d_bits)
+{
+    k_scale<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(src, dst, n, d_bits);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_ensure_scratch(s3d_engine *e, size_t elems)
+{
+    if (elems <= e->scratch_cap) return 0;
+    for (int i = 0; i < 2; i++) {
+        if (e->scratch[i]) cudaFree(e->scratch[i]);
+        e->scratch[i] = nullptr;
+    }
+    e->scratch_cap = 0;
+    for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaMalloc(&e->scratch[i], elems * sizeof(float)));
+    e->scratch_cap = elems;
+    return 0;
+}
+
+int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                   const TapSet &taps, const float uf[3]);  // blur_fused.cu
+bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps,
+                             const float uf[3]);
+
+int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz, int nc,
+               const TapSet &taps, const float uf[3])
+{
+    if (e->blur_mode == 0 && s3d_blur_fused_eligible(nx, ny, nz, nc, taps, uf))
+        return s3d_blur_fused(e, src, dst, nx, ny, nz, taps, uf);
+    const size_t total = (size_t)nx * ny * nz * nc;
+    if (s3d_ensure_scratch(e, total)) return -1;
+    const int grid = grid_for(e, total, 256, 16);
+    k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0]);
+    S3D_LAUNCH_CHECK(e);
+    k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
+                                               taps, uf[1]);
+    S3D_LAUNCH_CHECK(e);
+    k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2]);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_decimate(s3d_engine *e, const float *src, int sx, int sy, int sz, float *dst, int dx,
+                   int dy, int dz)
+{
+    (void)sz;
+    const size_t total = (size_t)dx * dy * dz;
+    k_decimate<<<grid_for(e, total, 256, 16), 256, 0, e->stream>>>(src, sx, sy, dst, dx, dy, dz);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_dog(s3d_engine *e, const float *a, const float *b, float *d, size_t n,
+              unsigned *d_maxbits)
+{
+    k_dog<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(a, b, d, n, d_maxbits);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_extrema_octave(s3d_engine *e, int o, float, double peak_thresh)
+{
+    const LevelDev &l0 = e->dog[(size_t)o * e->nlev_d];
+    const int nx = l0.g.nx, ny = l0.g.ny, nz = l0.g.nz;
+    const size_t total = (size_t)nx * ny * nz;
+    const int nblocks = (int)((total + EXT_BLOCK - 1) / EXT_BLOCK);
+    const size_t words = (size_t)nblocks * (EXT_BLOCK / 32);
+    const int K = e->K;
+    if (K > EXT_MAX_LEVELS) return s3d_fail(e, "num_kp_levels too large", cudaSuccess, __FILE__, __LINE__);
+    if (words * K > e->mask_cap) {
+        if (e->d_mask) cudaFree(e->d_mask);
+        e->d_mask = nullptr;
+        e->mask_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->d_mask, words * K * sizeof(unsigned)));
+        e->mask_cap = words * K;
+    }
+    if ((size_t)nblocks * K > e->blockcnt_cap) {
+        if (e->d_blockcnt) cudaFree(e->d_blockcnt);
+        e->d_blockcnt = nullptr;
+        e->blockcnt_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->d_blockcnt, (size_t)nblocks * K * sizeof(int)));
+        e->blockcnt_cap = (size_t)nblocks * K;
+    }
+    ExtLevels L;
+    for (int s = -1; s <= K; s++) L.dog[s + 1] = e->dog[(size_t)o * e->nlev_d + (s + 1)].d;
+    L.maxbits = e->d_scalars + 1 + (size_t)o * e->nlev_d;
+    L.K = K;
+    k_extrema_mark<<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
+                                                        e->d_blockcnt, nblocks, words);
+    S3D_LAUNCH_CHECK(e);
+    k_extrema_scan<<<1, 1024, 0, e->stream>>>(e->d_blockcnt, nblocks, K, e->d_counter);
+    S3D_LAUNCH_CHECK(e);
+    k_extrema_emit<<<nblocks, EXT_BLOCK, 0, e->stream>>>(e->d_mask, e->d_blockcnt, nblocks, words,
+                                                        K, o, nx, ny, nz, e->d_cand, e->cand_cap);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}

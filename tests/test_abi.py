@@ -1,0 +1,205 @@
+"""CPU tests of the drop-in boundary: the C-ABI libraries load, export every symbol
+the headers declare, keep the reference's struct layout and error behaviour, and
+refuse to compute without a CUDA device (no CPU fallback).  No GPU compute here."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import HAVE_GPU, REPO
+
+
+def test_struct_sizes_match_reference_abi():
+    from sift3d_b200 import capi
+    for t, n in capi.ABI_SIZES.items():
+        assert C.sizeof(t) == n
+    assert capi.SIFT3D.gpyr.offset == 80 and capi.SIFT3D.dog.offset == 128
+    assert capi.SIFT3D.im.offset == 176 and capi.SIFT3D.peak_thresh.offset == 280
+    assert capi.Keypoint.R.offset == 40 and capi.Keypoint.xd.offset == 72
+    assert capi.Image.nx.offset == 32 and capi.Image.xs.offset == 72 and capi.Image.nc.offset == 96
+
+
+def test_libsift3d_exports_every_sift_h_symbol(b200_lib):
+    from sift3d_b200 import capi
+    missing = [s for s in capi.SIFT_H_SYMBOLS if not b200_lib.exports(s)]
+    assert not missing, missing
+    # the reference also exports its default constants (sift.c:34-45)
+    for sym in ("peak_thresh_default", "corner_thresh_default", "sigma0_default", "opt_sigma0"):
+        assert b200_lib.exports(sym), sym
+    assert C.c_double.in_dll(b200_lib.lib, "peak_thresh_default").value == 0.1
+
+
+def test_cuda_shim_exports_every_declared_symbol(built):
+    """Every function declared in include/sift3d_cuda.h is exported by libsift3d_cuda.so."""
+    from sift3d_b200 import capi
+    hdr = (REPO / "include" / "sift3d_cuda.h").read_text()
+    names = set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"s3d_engine", "s3d_geom", "s3d_filter", "s3d_keypoint"}
+    lib = C.CDLL(str(capi.CUDA_LIB))
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert len(names) > 25 and not missing, missing
+
+
+def test_abi_header_symbols_exported(b200_lib):
+    hdr = (REPO / "include" / "sift3d_abi.h").read_text()
+    decl = hdr[hdr.index("/* ---- sift3d/sift.h:19-108"):]
+    names = set(re.findall(r"^(?:int|void|void \*)\s*\*?([A-Za-z_][A-Za-z0-9_]*)\(", decl, re.M))
+    assert len(names) >= 35, names
+    missing = [n for n in sorted(names) if not b200_lib.exports(n)]
+    assert not missing, missing
+
+
+def test_same_symbol_set_as_reference(b200_lib, ref_lib):
+    """nm -D of the reference's libsift3D vs ours: every T/D symbol of the reference exists."""
+    def syms(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", str(path)], capture_output=True,
+                             text=True, check=True).stdout
+        return {ln.split()[-1] for ln in out.splitlines() if ln.split()[1] in "TDRB"}
+    ref = syms(ref_lib.path)
+    ours = syms(b200_lib.path)
+    allowed_missing = {"bary_eps", "desc_rad_fctr", "max_eig_ratio", "ori_grad_thresh",
+                       "ori_rad_fctr", "ori_sig_fctr", "trunc_thresh", "SIFT3D_desc_acc_interp"}
+    assert not (ref - ours - allowed_missing), sorted(ref - ours - allowed_missing)
+
+
+def test_init_params_and_validation_without_gpu(b200_lib):
+    """init_SIFT3D / setters are host logic (sift.c:514-626) and work without a device."""
+    from sift3d_b200 import capi
+    s = capi.SIFT3D()
+    L = b200_lib.lib
+    assert L.init_SIFT3D(C.byref(s)) == 0
+    assert s.peak_thresh == 0.1 and s.corner_thresh == 0.4 and s.dense_rotate == 0
+    assert s.gpyr.num_kp_levels == 3 and s.gpyr.num_levels == 6 and s.dog.num_levels == 5
+    assert s.gpyr.first_level == -1 and s.gpyr.num_octaves == 0
+    assert s.gpyr.sigma0 == 1.6 and s.gpyr.sigma_n == 1.15
+    assert L.SIFT3D_have_gpyr(C.byref(s)) == 0
+    assert L.set_peak_thresh_SIFT3D(C.byref(s), 0.0) == -1   # (0, 1]
+    assert L.set_peak_thresh_SIFT3D(C.byref(s), 1.5) == -1
+    assert L.set_peak_thresh_SIFT3D(C.byref(s), 0.25) == 0 and s.peak_thresh == 0.25
+    assert L.set_corner_thresh_SIFT3D(C.byref(s), -0.1) == -1  # [0, 1]
+    assert L.set_corner_thresh_SIFT3D(C.byref(s), 1.0) == 0
+    assert L.set_sigma_n_SIFT3D(C.byref(s), -1.0) == -1
+    assert L.set_num_kp_levels_SIFT3D(C.byref(s), 4) == 0
+    assert s.gpyr.num_levels == 7 and s.dog.num_levels == 6
+    L.cleanup_SIFT3D(C.byref(s))
+
+
+def test_keypoint_store_slab_semantics(b200_lib):
+    """resize_Keypoint_store grows in 500-element slabs and re-aliases R (sift.c:417-436)."""
+    from sift3d_b200 import capi
+    L = b200_lib.lib
+    kp = capi.Keypoint_store()
+    L.init_Keypoint_store(C.byref(kp))
+    assert L.resize_Keypoint_store(C.byref(kp), 3) == 0
+    assert kp.slab.num == 3 and kp.slab.buf_size == 500 * 112
+    for i in range(3):
+        k = kp.buf[i]
+        assert k.R.data == C.addressof(k.r_data) and k.R.static_mem == 1
+        assert k.R.num_rows == 3 and k.R.num_cols == 3 and k.R.type == 1 and k.R.size == 36
+    assert L.resize_Keypoint_store(C.byref(kp), 501) == 0 and kp.slab.buf_size == 1000 * 112
+    assert L.resize_Keypoint_store(C.byref(kp), 0) == 0 and kp.slab.buf_size == 0 and not kp.slab.buf
+    L.cleanup_Keypoint_store(C.byref(kp))
+
+
+def test_descriptor_matrix_roundtrip_and_nn_match(b200_lib):
+    """Converters + SIFT3D_nn_match are host code: Mat_rm round trip, forward/backward match."""
+    from sift3d_b200 import capi
+    L = b200_lib.lib
+    rng = np.random.default_rng(0)
+    n = 40
+    rows = np.zeros((n, 771), np.float32)
+    rows[:, :3] = rng.uniform(0, 50, (n, 3))
+    rows[:, 3:] = rng.random((n, 768))
+    m = capi.Mat_rm()
+    m.data = rows.ctypes.data
+    m.size = rows.nbytes
+    m.num_cols, m.num_rows, m.static_mem, m.type = 771, n, 1, 1
+    d1 = capi.SIFT3D_Descriptor_store()
+    L.init_SIFT3D_Descriptor_store(C.byref(d1))
+    L.Mat_rm_to_SIFT3D_Descriptor_store.argtypes = [C.POINTER(capi.Mat_rm),
+                                                    C.POINTER(capi.SIFT3D_Descriptor_store)]
+    assert L.Mat_rm_to_SIFT3D_Descriptor_store(C.byref(m), C.byref(d1)) == 0
+    assert d1.num == n and d1.buf[3].xd == rows[3, 0] and d1.buf[3].sd == 1.6
+    back = capi.Mat_rm()
+    C.memset(C.byref(back), 0, C.sizeof(back))
+    back.type = 1
+    L.SIFT3D_Descriptor_store_to_Mat_rm.argtypes = [C.POINTER(capi.SIFT3D_Descriptor_store),
+                                                    C.POINTER(capi.Mat_rm)]
+    assert L.SIFT3D_Descriptor_store_to_Mat_rm(C.byref(d1), C.byref(back)) == 0
+    got = np.ctypeslib.as_array(C.cast(back.data, C.POINTER(C.c_float)), shape=(n, 771))
+    assert np.array_equal(got, rows)
+    # second set = permuted copy with tiny noise -> nn_match must recover the permutation
+    perm = rng.permutation(n)
+    rows2 = rows[perm].copy()
+    rows2[:, 3:] += 1e-4 * rng.random((n, 768)).astype(np.float32)
+    m2 = capi.Mat_rm()
+    m2.data = rows2.ctypes.data
+    m2.size = rows2.nbytes
+    m2.num_cols, m2.num_rows, m2.static_mem, m2.type = 771, n, 1, 1
+    d2 = capi.SIFT3D_Descriptor_store()
+    L.init_SIFT3D_Descriptor_store(C.byref(d2))
+    assert L.Mat_rm_to_SIFT3D_Descriptor_store(C.byref(m2), C.byref(d2)) == 0
+    matches = C.POINTER(C.c_int)()
+    assert L.SIFT3D_nn_match(C.byref(d1), C.byref(d2), C.c_float(0.8), C.byref(matches)) == 0
+    got = np.array([matches[i] for i in range(n)])
+    inv = np.argsort(perm)
+    assert np.array_equal(got, inv)
+    b200_lib._libc.free(C.cast(matches, C.c_void_p))
+    b200_lib._libc.free(back.data)
+    L.cleanup_SIFT3D_Descriptor_store(C.byref(d1))
+    L.cleanup_SIFT3D_Descriptor_store(C.byref(d2))
+
+
+def test_nn_match_equals_reference(b200_lib, ref_lib):
+    from sift3d_b200 import capi
+    rng = np.random.default_rng(5)
+
+    def store(lib, rows):
+        m = capi.Mat_rm()
+        m.data = rows.ctypes.data
+        m.size = rows.nbytes
+        m.num_cols, m.num_rows, m.static_mem, m.type = 771, len(rows), 1, 1
+        d = capi.SIFT3D_Descriptor_store()
+        lib.lib.init_SIFT3D_Descriptor_store(C.byref(d))
+        lib.lib.Mat_rm_to_SIFT3D_Descriptor_store.argtypes = [
+            C.POINTER(capi.Mat_rm), C.POINTER(capi.SIFT3D_Descriptor_store)]
+        assert lib.lib.Mat_rm_to_SIFT3D_Descriptor_store(C.byref(m), C.byref(d)) == 0
+        return d
+    a = rng.random((60, 771)).astype(np.float32)
+    b = np.concatenate([a[:30] + 0.02 * rng.random((30, 771)).astype(np.float32),
+                        rng.random((25, 771)).astype(np.float32)])
+    res = []
+    for lib in (b200_lib, ref_lib):
+        d1, d2 = store(lib, a), store(lib, b)
+        m = C.POINTER(C.c_int)()
+        assert lib.lib.SIFT3D_nn_match(C.byref(d1), C.byref(d2), C.c_float(0.8), C.byref(m)) == 0
+        res.append(np.array([m[i] for i in range(60)]))
+    assert np.array_equal(res[0], res[1]) and (res[0] >= 0).sum() >= 25
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-device failure mode")
+def test_hot_path_fails_loudly_without_cuda(b200_lib, capfd):
+    """No CPU fallback: without a CUDA device the hot calls return SIFT3D_FAILURE."""
+    from sift3d_b200 import capi
+    vol = np.random.default_rng(0).random((16, 16, 16), dtype=np.float32)
+    with capi.Sift3D(b200_lib) as s:
+        with pytest.raises(RuntimeError):
+            s.detect_keypoints(vol)
+        assert b200_lib.lib.SIFT3D_have_gpyr(C.byref(s.s)) == 0
+    err = capfd.readouterr().err
+    assert "no CPU fallback" in err or "CUDA" in err
+
+
+def test_product_never_touches_the_oracle():
+    """The shipped path must not import/link anything under oracle/."""
+    for f in list((REPO / "sift3d_b200" / "csrc").glob("*")) + \
+            list((REPO / "sift3d_b200" / "host").glob("*")) + [REPO / "sift3d_b200" / "capi.py"]:
+        txt = f.read_text()
+        assert "oracle/" not in txt.replace("oracle/_ref", "").replace("tests/", "") or \
+            f.name == "capi.py", f
+    from sift3d_b200 import capi
+    out = subprocess.run(["ldd", str(capi.B200_LIB)], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "_ref" not in out
