@@ -55,6 +55,7 @@ struct s3d_engine {
     std::string err;
     long long launches = 0;
     int blur_mode = 0;
+    int opt_icos_fast = 1;
 
     // pyramid
     int noct = 0, K = 0, nlev_g = 0, nlev_d = 0;

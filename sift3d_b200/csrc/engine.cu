@@ -198,6 +198,14 @@ int s3d_set_blur_mode(s3d_engine *e, int mode)
     return 0;
 }
 
+int s3d_set_option(s3d_engine *e, const char *name, int value)
+{
+    if (!strcmp(name, "icos_fast")) e->opt_icos_fast = value;
+    else if (!strcmp(name, "blur_mode")) e->blur_mode = value;
+    else return s3d_fail(e, "s3d_set_option: unknown option", cudaSuccess, __FILE__, __LINE__);
+    return 0;
+}
+
 int s3d_set_mesh(s3d_engine *e, const float *v, const int *idx)
 {
     DeviceGuard guard(e->device);

@@ -52,7 +52,7 @@ __device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], 
 // other face can pass (faces only overlap within bary_eps of shared edges), so
 // it is also the first.  Otherwise fall back to the literal in-order loop.
 __device__ __forceinline__ int icos_bin(const MeshDev *__restrict__ M, const float g[3],
-                                        float bary[3])
+                                        float bary[3], const bool fast = true)
 {
     const float n2 = fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2]));
     if ((double)n2 < K_BARY_EPS) return -1;
@@ -68,7 +68,7 @@ __device__ __forceinline__ int icos_bin(const MeshDev *__restrict__ M, const flo
         }
     }
     const float margin = 1e-4f;
-    if (face_test(M->f[best], g, bary) && bary[0] > margin && bary[1] > margin &&
+    if (fast && face_test(M->f[best], g, bary) && bary[0] > margin && bary[1] > margin &&
         bary[2] > margin)
         return best;
     for (int i = 0; i < 20; i++)
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(DESC_THREADS)
     k_descriptor(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
-                 const MeshDev *__restrict__ M, unsigned char *__restrict__ out)
+                 const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
     __shared__ float hist[S3D_DESC_NUMEL];
     __shared__ double s_red[DESC_THREADS / 32];
@@ -418,7 +418,12 @@ __global__ void __launch_bounds__(DESC_THREADS)
         g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
         g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
         g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
-        const float w = expf(__fdiv_rn(fm(-0.5f, sq), s2));  // sift.c:1890 (f32 throughout)
+        // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument.  glibc's expf is
+        // correctly rounded in all but ~0.1 % of calls; CUDA's expf is only 2-ulp accurate, and a
+        // 1-ulp change of the weight can flip the icosahedron face of a gradient that sits within
+        // bary_eps of an edge (observed: one voxel in ~100 keypoints -> 2e-4 descriptor error).  A
+        // f64 exp rounded to f32 reproduces the correctly rounded value.
+        const float w = (float)exp((double)__fdiv_rn(fm(-0.5f, sq), s2));
         g[0] = fm(g[0], w);
         g[1] = fm(g[1], w);
         g[2] = fm(g[2], w);
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(DESC_THREADS)
         for (int a = 0; a < 3; a++)
             gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
         float bary[3];
-        const int bin = icos_bin(M, gr, bary);
+        const int bin = icos_bin(M, gr, bary, icos_fast != 0);
         if (bin < 0) continue;
         const float mag = __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
         float dv[3];
@@ -675,7 +680,7 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
     if (n <= 0) return 0;
     if (!e->have_mesh) return s3d_fail(e, "mesh not set", cudaSuccess, __FILE__, __LINE__);
     const PyrTable T = make_table(e);
-    k_descriptor<<<n, DESC_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+    k_descriptor<<<n, DESC_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out, e->opt_icos_fast);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

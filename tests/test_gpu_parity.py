@@ -225,7 +225,8 @@ def test_copy_sift3d_keeps_pyramid(b200_lib):
         assert b200_lib.lib.SIFT3D_have_gpyr(C.byref(b.s)) == 1
         assert np.array_equal(a.level_data("gpyr", 1, 2), b.level_data("gpyr", 1, 2))
         rc = b200_lib.lib.SIFT3D_extract_descriptors(C.byref(b.s), C.byref(a.kp), C.byref(b.desc))
-        assert rc == 0 and np.array_equal(b.descriptors()["hists"], da["hists"])
+        # histogram accumulation order is not fixed (shared-memory atomics): ~1e-7 run to run
+        assert rc == 0 and rel_l2(b.descriptors()["hists"], da["hists"]).max() <= 1e-6
 
 
 def test_full_size_properties(b200_lib):
@@ -241,7 +242,7 @@ def test_full_size_properties(b200_lib):
         d2 = s.extract_descriptors()
     assert len(kp1) > 1000 and s is not None
     assert np.array_equal(kp1.view(np.uint8), kp2.view(np.uint8))
-    assert np.array_equal(d1["hists"], d2["hists"])
+    assert rel_l2(d2["hists"], d1["hists"]).max() <= 1e-6  # atomics order only
     # (o, s, z, y, x) scan order (sift.c:1154, 1176)
     key = np.stack([kp1["o"], kp1["s"], kp1["zd"], kp1["yd"], kp1["xd"]], 1)
     order = np.lexsort(key.T[::-1])
