@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- voxels/s through pyramid + descriptors on B200 (BASELINE.json metric).
+
+One "step" = SIFT3D_detect_keypoints + SIFT3D_extract_descriptors over one synthetic
+512^3 float32 volume (BASELINE.json configs[1]; 7 octaves x 3 keypoint levels -- the
+octave count is not settable in the reference).
+
+  value      : device-resident throughput (volume already in HBM, results left in HBM),
+               timed with CUDA events on the launching stream, max over ranks.
+  e2e        : the same step through the drop-in C API (libsift3D.so) with HOST buffers:
+               H2D of the pinned volume and D2H of keypoints + descriptors inside the timed
+               region.
+  roofline   : the separable 3-D Gaussian (the dominant pyramid kernel): 8 B/voxel
+               algorithmic traffic / CUDA-event time of each launch, against
+               the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline: the reference's own OpenMP CPU path (oracle/_ref, unmodified sources) on
+               a bounded sample of the same workload, all host cores.
+
+N > 1 (torchrun): independent volumes, one per GPU (BASELINE.json configs[3]); no
+data-path collective, weak scaling; the only communication is the timing all-reduce.
+
+`--impl reference` times the reference CPU implementation instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "voxels/sec through pyramid+descriptors"
+UNIT = "voxels/s"
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
+
+
+def blob_volume_torch(n, seed, device):
+    """SURVEY.md Appendix C generator evaluated with torch (fast at 512^3): signed Gaussian
+    blobs at sigma 2,3,4,6,8 + 0.01*U[0,1) noise, shifted to min 0.  float32 [z][y][x]."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    vol = torch.zeros((n, n, n), dtype=torch.float32, device=device)
+    for sig in (2, 3, 4, 6, 8):
+        k = max(1, int(n ** 3 / (64 * sig ** 3)))
+        idx = torch.randint(0, n, (k, 3), generator=g)
+        amp = (torch.rand(k, generator=g) * 2 - 1).float() * sig ** 3
+        imp = torch.zeros((n, n, n), dtype=torch.float32, device=device)
+        imp.index_put_((idx[:, 0].to(device), idx[:, 1].to(device), idx[:, 2].to(device)),
+                       amp.to(device), accumulate=True)
+        r = int(4 * sig)
+        x = torch.arange(-r, r + 1, dtype=torch.float32, device=device)
+        w = torch.exp(-0.5 * (x / sig) ** 2)
+        w = w / w.sum()
+        t = imp[None, None]
+        for ax in range(3):
+            shape = [1, 1, 1, 1, 1]
+            shape[2 + ax] = 2 * r + 1
+            pad = [0, 0, 0, 0, 0, 0]
+            pad[2 * (2 - ax)] = pad[2 * (2 - ax) + 1] = r
+            t = F.conv3d(F.pad(t, pad, mode="reflect"), w.view(shape))
+        vol += t[0, 0]
+        del imp, t
+    noise = torch.rand((n, n, n), generator=g, dtype=torch.float32)
+    vol += 0.01 * noise.to(device)
+    vol -= vol.min()
+    return vol.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.gpu = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def hbm_peak():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def pyramid_filters():
+    """sigma and width of the default pyramid's filters."""
+    s = [1.6 * 2 ** (k / 3.0) for k in range(-1, 5)]
+    sig = [float(np.sqrt(s[0] ** 2 - 1.15 ** 2))] + [float(np.sqrt(s[i + 1] ** 2 - s[i] ** 2))
+                                                     for i in range(5)]
+    return sig
+
+
+def gauss_taps(sigma):
+    """init_Gauss_filter (imutil.c:3657-3710) restated for the bench's kernel-level timing."""
+    hw = max(int(np.ceil(sigma * 3.0)), 1)
+    x = (np.arange(2 * hw + 1, dtype=np.float64) - hw) / (sigma + np.finfo(np.float64).eps)
+    k = np.exp(-0.5 * x * x).astype(np.float32)
+    acc = np.float32(0)
+    for v in k:
+        acc = np.float32(acc + v)
+    return (k / acc).astype(np.float32)
+
+
+def cpu_reference_run(n_sample, seed, threads=None):
+    """Time the reference's own CPU path (oracle/_ref) -- or the oracle port if _ref is
+    absent -- on an n_sample^3 volume of the same generator.  Returns (voxels/s, info)."""
+    from sift3d_b200 import capi
+    from sift3d_b200.volumes import blob_volume
+    vol = blob_volume(n_sample, seed=seed)
+    cores = threads or os.cpu_count()
+    if capi.REF_LIB.exists():
+        ref = capi.load_reference()
+        with capi.Sift3D(ref) as s:
+            t0 = time.perf_counter()
+            kp = s.detect_keypoints(vol)
+            t1 = time.perf_counter()
+            if len(kp):
+                s.extract_descriptors()
+            t2 = time.perf_counter()
+        kind = "reference"
+    else:
+        from sift3d_b200.oracle_api import Oracle
+        orc = Oracle()
+        t0 = time.perf_counter()
+        kp = orc.detect(vol)
+        t1 = time.perf_counter()
+        if len(kp):
+            orc.describe(kp)
+        t2 = time.perf_counter()
+        kind = "port"
+    return vol.size / (t2 - t0), dict(kind=kind, cores=cores, detect_s=t1 - t0, describe_s=t2 - t1,
+                                      keypoints=int(len(kp)),
+                                      sample=f"{n_sample}^3 blob volume (seed {seed}), detect+describe, "
+                                             f"OMP threads={cores}")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_size
+    times, info = [], None
+    for it in range(args.warmup + args.steps):
+        v, info = cpu_reference_run(n, seed=1234 + it % 4)
+        if it >= args.warmup:
+            times.append(n ** 3 / v)
+    ms = 1e3 * float(np.mean(times))
+    value = n ** 3 / (ms * 1e-3)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bounded sample of configs[1]: {n}^3 synthetic float32 volume per step "
+                               "(reference CPU path cannot do 512^3 within minutes), kpSift3D defaults"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="edge of the synthetic volume")
+    ap.add_argument("--ref-size", type=int, default=128, help="edge of the CPU-arm sample volume")
+    ap.add_argument("--cpu-sample", type=int, default=160, help="edge of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blur-reps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    from sift3d_b200 import capi
+    from sift3d_b200.engine_api import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["SIFT3D_CUDA_DEVICE"] = str(local_rank)
+
+    n = args.size
+    nvox = n ** 3
+    vol_dev = blob_volume_torch(n, seed=1234 + rank, device=dev)   # per-rank independent volume
+    vol_pinned = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
+    vol_pinned.copy_(vol_dev)
+    vol_host = vol_pinned.numpy()
+    torch.cuda.synchronize()
+
+    lib = capi.load_b200()
+    cu = C.CDLL(str(capi.CUDA_LIB))
+    lib.lib.sift3d_b200_engine.restype = C.c_void_p
+    lib.lib.sift3d_b200_engine.argtypes = [C.POINTER(capi.SIFT3D)]
+    for f, at in (("s3d_image_from_device", [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+                  ("s3d_build_pyramid", [C.c_void_p]),
+                  ("s3d_detect_extrema", [C.c_void_p, C.c_double, C.POINTER(C.c_int)]),
+                  ("s3d_assign_orientations", [C.c_void_p, C.c_double, C.POINTER(C.c_int)]),
+                  ("s3d_extract_descriptors_device", [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+                  ("s3d_engine_set_stream", [C.c_void_p, C.c_void_p]),
+                  ("s3d_engine_launch_count", [C.c_void_p])):
+        getattr(cu, f).argtypes = at
+    cu.s3d_device_keypoints.argtypes = [C.c_void_p]
+    cu.s3d_device_keypoints.restype = C.c_void_p
+    cu.s3d_engine_launch_count.restype = C.c_longlong
+
+    s = capi.Sift3D(lib)
+    # a real (non-NULL) stream: the engine launches on it and the events below bracket it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def e2e_step():
+        kp = s.detect_keypoints(vol_host)           # H2D inside (pinned source)
+        d = s.extract_descriptors() if len(kp) else None   # D2H of descriptors inside
+        return len(kp), (0 if d is None else d.nbytes) + kp.nbytes
+
+    # first call creates the engine, sizes the pyramid and warms every kernel
+    nkp, d2h = e2e_step()
+    eng = lib.lib.sift3d_b200_engine(C.byref(s.s))
+    cu.s3d_engine_set_stream(eng, C.c_void_p(stream.cuda_stream))
+    desc_dev = torch.empty(max(nkp, 1) * 3104 + 4096, dtype=torch.uint8, device=dev)
+
+    def dev_step():
+        nc, nk = C.c_int(0), C.c_int(0)
+        rc = cu.s3d_image_from_device(eng, vol_dev.data_ptr(), n, n, n)
+        rc |= cu.s3d_build_pyramid(eng)
+        rc |= cu.s3d_detect_extrema(eng, s.s.peak_thresh, C.byref(nc))
+        rc |= cu.s3d_assign_orientations(eng, s.s.corner_thresh, C.byref(nk))
+        if nk.value > 0:
+            if nk.value * 3104 > desc_dev.numel():
+                raise RuntimeError("descriptor buffer too small")
+            rc |= cu.s3d_extract_descriptors_device(eng, cu.s3d_device_keypoints(eng), nk.value,
+                                                    desc_dev.data_ptr())
+        if rc:
+            raise RuntimeError("device step failed")
+        return nc.value, nk.value
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ---------------------------------------------------
+    for _ in range(args.warmup):
+        ncand, nkp = dev_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = cu.s3d_engine_launch_count(eng)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        ncand, nkp = dev_step()
+    ev1.record(stream)
+    barrier()
+    launches = int(cu.s3d_engine_launch_count(eng) - l0)
+    ms_dev = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- end-to-end timing through the C API with host buffers -----------------------------
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record(stream)
+    for _ in range(args.steps):
+        nkp_e, d2h = e2e_step()
+    ee1.record(stream)
+    barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+
+    # max over ranks
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the separable Gaussian (rank 0) ---------------------------------------
+    roof = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        e2 = Engine(local_rank)
+        e2.set_stream(C.c_void_p(stream.cuda_stream))
+        src = vol_dev
+        dst = torch.empty_like(vol_dev)
+        per = []
+        tot_ms, tot_bytes = 0.0, 0.0
+        for sg in pyramid_filters():
+            taps = gauss_taps(sg)
+            for _ in range(3):
+                e2.blur_device(src.data_ptr(), dst.data_ptr(), n, n, n, taps)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(args.blur_reps):
+                e2.blur_device(src.data_ptr(), dst.data_ptr(), n, n, n, taps)
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / args.blur_reps
+            gbs = 8.0 * nvox / (ms * 1e-3) / 1e9
+            per.append({"width": int(len(taps)), "ms": round(ms, 4), "gbs": round(gbs, 1),
+                        "frac": round(gbs / peak, 4)})
+            tot_ms += ms
+            tot_bytes += 8.0 * nvox
+        ach = tot_bytes / (tot_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "separable 3-D Gaussian blur (6 octave-0 filters of the pyramid)",
+                "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": 8.0 * nvox,
+                "per_filter": per}
+        e2.close()
+        del dst
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, info = cpu_reference_run(args.cpu_sample, seed=1234)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+               "sample": info["sample"], "detect_s": round(info["detect_s"], 2),
+               "describe_s": round(info["describe_s"], 2), "keypoints": info["keypoints"]}
+
+    s.close()
+    if rank == 0:
+        value = nvox * world / (ms_dev * 1e-3)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"single {n}^3 synthetic float32 volume per GPU (configs[1]; "
+                                   f"configs[3] at N>1), 7 octaves x 3 keypoint levels, kpSift3D defaults",
+                       "candidates": ncand, "keypoints": nkp,
+                       "l2_note": f"inputs ({4 * nvox >> 20} MiB/level) larger than the 126 MB L2",
+                       "parallelism": f"independent volumes x{world}, no data-path collective"},
+            "e2e": {"value": nvox * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 4 * nvox, "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if roof is not None:
+            out["roofline"] = roof
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,11 +1,496 @@
-// blur_fused.cu -- fused X/Y/Z separable Gaussian (fast path).  Placeholder until
-// the generic path is parity-green on the GPU.
+// blur_fused.cu -- fused X/Y/Z separable Gaussian for sm_100a (the pyramid's hot kernel).
+//
+// Replaces apply_Sep_FIR_filter (imutil.c:3459-3544) = copy + [permute, convolve_sep_gen
+// (imutil.c:2274-2393), permute] x 3 for the case every octave-0 pyramid level hits:
+// one channel, tap spacing exactly 1 voxel on all three axes (unit / units == 1).
+// HBM traffic is the algorithmic minimum, 8 B/voxel (read once, write once); the
+// x- and y-filtered intermediates never leave the SM.
+//
+// Bit-exactness.  With integer tap spacing every sample coordinate c = i - d is an
+// integer, so the reference's per-tap expression tap*((1-frac)*lo + frac*hi) reduces to
+// tap*S(c) where S is the line extended by the reference's boundary rules
+// (imutil.c:2365-2387):   S(j) = src[-j]                       j < 0
+//                         S(j) = src[j]                        0 <= j < n-1
+//                         S(j) = (1-f)*src[lo] + f*src[lo+1]   j >= n-1, c' = 2(n-1) - j - 0.1,
+//                                                              lo = (int)c', f = c' - lo
+// (for j < n-1 the "+ 0*hi" term adds an exact zero).  Each axis is therefore a plain FIR
+// over an extended line, accumulated in the reference's order d = -hw..hw (= descending
+// sample index) with separately rounded multiply and add.
+//
+// Structure.  A CTA owns a 64x32 (x,y) column and marches DOWN in z:
+//   fill   global -> registers (two 16-byte loads per thread, issued one plane ahead, right
+//          after the X phase) -> smem tile A (halo in x and y), rows pair-interleaved
+//   X      each thread: 4 outputs along x for a PAIR of rows  (A -> smem B)
+//   Y      each thread: its own 2 rows x 1 x-pair             (B -> registers)
+//   Z      transposed-form FIR: 2hw+1 running partial sums per owned voxel live in
+//          registers; each new xy-filtered plane updates all of them and retires one
+//          output plane (coalesced 8-byte stores).  Descending z makes every output
+//          accumulate its taps in the reference's order.
+// All arithmetic is packed FFMA2 (fma.rn.f32x2): a*b+(-0) is the exactly rounded product,
+// a*1+c the exactly rounded sum, two voxels per instruction -- measured 2x the scalar
+// FMUL+FADD rate on B200 (tools/ubench.cu).  The tap symmetry t[a] == t[2hw-a] lets the Z
+// phase share products: (hw+1) multiplies + (2hw+1) adds per voxel pair.
 #include "common.cuh"
 
-bool s3d_blur_fused_eligible(int, int, int, int, const TapSet &, const float[3]) { return false; }
+#include <algorithm>
+#include <cmath>
+#include <cstring>
 
-int s3d_blur_fused(s3d_engine *e, const float *, float *, int, int, int, const TapSet &,
-                   const float[3])
+namespace {
+
+constexpr int TX = 64, TY = 32, NT = 512;
+constexpr int MAXHW = 8;
+constexpr int APITCH = 82;  // float2 per row pair of A; 8*APITCH % 128 == 16 -> conflict-free LDS.128
+constexpr int BPITCH = 68;  // floats per row of B (16-byte aligned rows)
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk(float lo, float hi)
 {
-    return s3d_fail(e, "fused blur not built", cudaSuccess, __FILE__, __LINE__);
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+struct Consts {
+    u64 nz, one, pz;  // (-0,-0), (1,1), (+0,+0)
+};
+// exactly rounded product / sum of two packed pairs
+__device__ __forceinline__ u64 mul2(u64 a, u64 t, const Consts &k) { return fma2(a, t, k.nz); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b, const Consts &k) { return fma2(a, k.one, b); }
+
+struct Seg {
+    int x0, y0, za, zb;
+};
+
+struct MirrorTab {  // right-hand mirror samples j = n-1+k, k = 0..MAXHW (host-computed, f32)
+    int lo[MAXHW + 1];
+    float f[MAXHW + 1], omf[MAXHW + 1];
+};
+
+struct FusedParams {
+    const float *src;
+    float *dst;
+    int nx, ny, nz;
+    const Seg *segs;
+    const int *seg_start;  // per CTA: [seg_start[b], seg_start[b+1])
+    MirrorTab mx, my, mz;
+    TapSet taps;
+    // -0.0f / 1.0f / +0.0f passed at run time: with literal constants ptxas folds
+    // fma(a,t,-0) -> mul and fma(p,1,c) -> add and then CONTRACTS the pair into one FFMA2
+    // (observed in SASS; -fmad=false does not cover f32x2), which would break bit-exactness.
+    float c_negzero, c_one, c_zero;
+};
+
+enum { MODE_NORMAL = 0, MODE_STASH = 1, MODE_LERP = 2 };
+
+template <int HW>
+__global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
+{
+    constexpr int W = 2 * HW + 1;
+    constexpr int HWA = (HW + 3) & ~3;   // x halo rounded up so that 16-byte loads stay aligned
+    constexpr int NR = TY + 2 * HW;      // rows of the A/B tiles (even)
+    constexpr int NRP = NR / 2;          // row pairs
+    constexpr int AW = TX + 2 * HWA;     // columns of the A tile
+    constexpr int AWQ = AW / 4;          // 4-column groups per row
+    constexpr int D0 = (HWA - HW) & ~1;  // even column where the X window of run 0 starts
+    constexpr int SH = (HWA - HW) & 1;   // 1 if the true window starts one column later
+    constexpr int LW = 2 * HW + 4 + 2 * SH;  // window length (even)
+    static_assert(NRP * AWQ <= NT, "one fill item per thread");
+    static_assert(NRP <= 32, "row pairs map to lanes");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *A = reinterpret_cast<float2 *>(smem_raw);
+    float *B = reinterpret_cast<float *>(A + NRP * APITCH);
+    short *task_plane = reinterpret_cast<short *>(B + NR * BPITCH);  // [<= nz + 2HW + 2]
+    unsigned char *task_mode = reinterpret_cast<unsigned char *>(task_plane + (P.nz + 2 * HW + 4));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nx = P.nx, ny = P.ny, nz = P.nz;
+    const size_t plane_stride = (size_t)nx * ny;
+    Consts K;
+    K.nz = pk(P.c_negzero, P.c_negzero);
+    K.one = pk(P.c_one, P.c_one);
+    K.pz = pk(P.c_zero, P.c_zero);
+    // lanes 4..7 of every quarter warp swap the order of their two 16-byte stores so that
+    // the eight lanes of a quarter hit eight different bank groups (see fill / X store)
+    const bool swap_st = (lane & 4) != 0;
+
+    for (int si = P.seg_start[blockIdx.x]; si < P.seg_start[blockIdx.x + 1]; si++) {
+        const Seg sg = P.segs[si];
+        const int x0 = sg.x0, y0 = sg.y0;
+        const bool ybound = (y0 - HW < 0) || (y0 + TY + HW > ny - 1);
+        const bool xbound = (x0 - HW < 0) || (x0 + TX + HW > nx - 1);
+        // ---- task list: samples j = zb-1+HW .. za-HW of the extended z line --------------
+        __syncthreads();
+        int ntask;
+        {
+            const int dim_end = nz - 1;
+            const int jt = sg.zb - 1 + HW, jb = sg.za - HW;
+            const int nlerp = jt >= dim_end ? jt - dim_end + 1 : 0;
+            ntask = (jt - jb + 1) + (nlerp ? 1 : 0);
+            for (int t = tid; t < ntask; t += NT) {
+                int plane, mode;
+                if (nlerp && t == 0) {
+                    plane = P.mz.lo[jt - dim_end];  // = 2*dim_end - jt - 1
+                    mode = MODE_STASH;
+                } else {
+                    const int j = jt - (t - (nlerp ? 1 : 0));
+                    if (j >= dim_end) {
+                        plane = P.mz.lo[j - dim_end] + 1;
+                        mode = MODE_LERP | ((j - dim_end) << 2);
+                    } else {
+                        plane = j < 0 ? -j : j;
+                        mode = MODE_NORMAL;
+                    }
+                }
+                task_plane[t] = (short)plane;
+                task_mode[t] = (unsigned char)mode;
+            }
+        }
+
+        // ---- per-thread fill item: row pair frp, columns 4*fq..4*fq+3 of the A tile --------
+        const bool fill_thread = tid < NRP * AWQ;
+        const int frp = tid / AWQ, fq = tid - frp * AWQ;
+        const int fy = y0 - HW + 2 * frp;        // global row of the pair's first row
+        const int fx = x0 - HWA + 4 * fq;        // global column of the group's first column
+        const bool cols_in = fx >= 0 && fx + 3 <= nx - 1;   // group inside the volume (x0, nx, HWA % 4 == 0)
+        const bool row0_ok = fill_thread && cols_in && fy >= 0 && fy < ny;
+        const bool row1_ok = fill_thread && cols_in && fy + 1 >= 0 && fy + 1 < ny;
+        const float *g0 = P.src + (size_t)(row0_ok ? fy : 0) * nx;
+        const float *g1 = P.src + (size_t)(row1_ok ? fy + 1 : 0) * nx;
+        float2 *fdst = A + frp * APITCH + 4 * fq;
+
+        // one row of the group: a single aligned 16-byte load; groups that lie outside
+        // [0, nx) are skipped and synthesised in shared memory by the X-mirror patch
+        auto load4 = [&](const float *row, bool ok) -> float4 {
+            if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
+            return __ldg(reinterpret_cast<const float4 *>(row + fx));
+        };
+        auto store_item = [&](const float4 a, const float4 b) {
+            if (!fill_thread) return;
+            const float4 lo4 = make_float4(a.x, b.x, a.y, b.y), hi4 = make_float4(a.z, b.z, a.w, b.w);
+            float4 *d = reinterpret_cast<float4 *>(fdst);
+            if (swap_st) {
+                d[1] = hi4;
+                d[0] = lo4;
+            } else {
+                d[0] = lo4;
+                d[1] = hi4;
+            }
+        };
+
+        u64 acc[2][W];  // Z-phase partial sums by age, for the thread's two rows
+        u64 prevY[2];
+#pragma unroll
+        for (int a = 0; a < W; a++) acc[0][a] = acc[1][a] = K.pz;
+        prevY[0] = prevY[1] = K.pz;
+        __syncthreads();  // task table visible
+
+        {   // first plane
+            const size_t off = (size_t)task_plane[0] * plane_stride;
+            store_item(load4(g0 + off, row0_ok), load4(g1 + off, row1_ok));
+        }
+        // output pointer of z = zb + 2HW (moved down one plane per z step)
+        float *optr = P.dst + ((size_t)(sg.zb + 2 * HW) * ny + (y0 + 2 * warp)) * nx + x0 + 2 * lane;
+        int zout = sg.zb + 2 * HW;
+        for (int t = 0; t < ntask; t++) {
+            __syncthreads();  // S1: A holds plane t; B free
+
+            if (xbound) {  // mirror columns of A outside [0, nx-1) (block-uniform branch)
+                const int nl = x0 - HW < 0 ? HW - x0 : 0;                       // columns x < 0
+                const int nrt = x0 + TX + HW > nx - 1 ? x0 + TX + HW - (nx - 1) : 0;  // x >= nx-1
+                const int ncol = nl + nrt;
+                float *Af = reinterpret_cast<float *>(A);
+                float vals[3];
+                int idx[3], cnt = 0;
+                for (int e = tid; e < NR * ncol; e += NT) {
+                    const int r = e / ncol, c = e - r * ncol;
+                    const int base = ((r >> 1) * APITCH) * 2 + (r & 1);
+                    int xa;
+                    float v;
+                    if (c < nl) {  // x = c - HW ... : global x = x0 - HW + c < 0
+                        const int x = x0 - HW + c;
+                        xa = x - (x0 - HWA);
+                        v = Af[base + 2 * (-x - (x0 - HWA))];
+                    } else {
+                        const int k = c - nl;  // x = nx-1+k
+                        xa = nx - 1 + k - (x0 - HWA);
+                        const int lo = P.mx.lo[k] - (x0 - HWA);
+                        v = __fadd_rn(__fmul_rn(P.mx.omf[k], Af[base + 2 * lo]),
+                                      __fmul_rn(P.mx.f[k], Af[base + 2 * (lo + 1)]));
+                    }
+                    idx[cnt] = base + 2 * xa;
+                    vals[cnt++] = v;
+                }
+                __syncthreads();
+                for (int q = 0; q < cnt; q++) Af[idx[q]] = vals[q];
+                __syncthreads();
+            }
+
+            // ---- X phase: warp = run of 4 outputs, lane = row pair --------------------------
+            if (lane < NRP) {
+                const float2 *arow = A + lane * APITCH + 4 * warp + D0;
+                u64 o0 = K.pz, o1 = K.pz, o2 = K.pz, o3 = K.pz;
+#pragma unroll
+                for (int kk = 0; kk < LW / 2; kk++) {
+                    const ulonglong2 v2 = *reinterpret_cast<const ulonglong2 *>(arow + (LW - 2 - 2 * kk));
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int p = LW - 1 - (2 * kk + h);   // window position, descending
+                        const u64 v = h == 0 ? v2.y : v2.x;
+                        // output i sits at window position SH + i + HW: tap index a = SH + i + 2HW - p
+                        const int a0 = SH + 2 * HW - p;
+                        if (a0 >= 0 && a0 < W) o0 = add2(mul2(v, pk(P.taps.t[a0 < 0 || a0 >= W ? 0 : a0], P.taps.t[a0 < 0 || a0 >= W ? 0 : a0]), K), o0, K);
+                        if (a0 + 1 >= 0 && a0 + 1 < W) o1 = add2(mul2(v, pk(P.taps.t[a0 + 1 < 0 || a0 + 1 >= W ? 0 : a0 + 1], P.taps.t[a0 + 1 < 0 || a0 + 1 >= W ? 0 : a0 + 1]), K), o1, K);
+                        if (a0 + 2 >= 0 && a0 + 2 < W) o2 = add2(mul2(v, pk(P.taps.t[a0 + 2 < 0 || a0 + 2 >= W ? 0 : a0 + 2], P.taps.t[a0 + 2 < 0 || a0 + 2 >= W ? 0 : a0 + 2]), K), o2, K);
+                        if (a0 + 3 >= 0 && a0 + 3 < W) o3 = add2(mul2(v, pk(P.taps.t[a0 + 3 < 0 || a0 + 3 >= W ? 0 : a0 + 3], P.taps.t[a0 + 3 < 0 || a0 + 3 >= W ? 0 : a0 + 3]), K), o3, K);
+                    }
+                }
+                float a0f, b0f, a1f, b1f, a2f, b2f, a3f, b3f;
+                upk(o0, a0f, b0f);
+                upk(o1, a1f, b1f);
+                upk(o2, a2f, b2f);
+                upk(o3, a3f, b3f);
+                float *brow = B + (2 * lane) * BPITCH + 4 * warp;
+                const float4 r0 = make_float4(a0f, a1f, a2f, a3f), r1 = make_float4(b0f, b1f, b2f, b3f);
+                if (swap_st) {
+                    *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
+                    *reinterpret_cast<float4 *>(brow) = r0;
+                } else {
+                    *reinterpret_cast<float4 *>(brow) = r0;
+                    *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
+                }
+            }
+            __syncthreads();  // S2: B complete, A free
+
+            // prefetch the next plane into registers; stored to A after the Z phase
+            float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+            const bool more = t + 1 < ntask;
+            if (more) {
+                const size_t off = (size_t)task_plane[t + 1] * plane_stride;
+                na = load4(g0 + off, row0_ok);
+                nb = load4(g1 + off, row1_ok);
+            }
+
+            if (ybound) {  // mirror rows of B outside [0, ny-1) (block-uniform branch)
+                const int nt_ = y0 - HW < 0 ? HW - y0 : 0;                          // rows y < 0
+                const int nb_ = y0 + TY + HW > ny - 1 ? y0 + TY + HW - (ny - 1) : 0;  // y >= ny-1
+                float vals[3];
+                int idx[3], cnt = 0;
+                for (int e = tid; e < (nt_ + nb_) * TX; e += NT) {
+                    const int rr = e / TX, x = e - rr * TX;
+                    if (rr < nt_) {  // tile row rr <-> y = y0 - HW + rr < 0; source row of -y
+                        const int y = y0 - HW + rr;
+                        idx[cnt] = rr * BPITCH + x;
+                        vals[cnt++] = B[(rr - 2 * y) * BPITCH + x];
+                    } else {
+                        const int k = rr - nt_;  // y = ny-1+k
+                        const int r = ny - 1 + k - (y0 - HW);
+                        const int rl = P.my.lo[k] - (y0 - HW);
+                        idx[cnt] = r * BPITCH + x;
+                        vals[cnt++] = __fadd_rn(__fmul_rn(P.my.omf[k], B[rl * BPITCH + x]),
+                                                __fmul_rn(P.my.f[k], B[(rl + 1) * BPITCH + x]));
+                    }
+                }
+                __syncthreads();
+                for (int q = 0; q < cnt; q++) B[idx[q]] = vals[q];
+                __syncthreads();
+            }
+
+            // ---- Y phase: rows y = 2*warp, 2*warp+1; x pair = lane ---------------------------
+            u64 y0acc = K.pz, y1acc = K.pz;
+            {
+                const float *bcol = B + (2 * warp + 1 + 2 * HW) * BPITCH + 2 * lane;
+#pragma unroll
+                for (int k = 0; k < W + 1; k++) {  // rows descending from 2*warp+1+HW
+                    const u64 v = *reinterpret_cast<const u64 *>(bcol - k * BPITCH);
+                    if (k < W) y1acc = add2(mul2(v, pk(P.taps.t[k < W ? k : 0], P.taps.t[k < W ? k : 0]), K), y1acc, K);
+                    if (k >= 1) y0acc = add2(mul2(v, pk(P.taps.t[k >= 1 ? k - 1 : 0], P.taps.t[k >= 1 ? k - 1 : 0]), K), y0acc, K);
+                }
+            }
+
+            // ---- Z phase --------------------------------------------------------------------
+            const int mode = task_mode[t];
+            if ((mode & 3) == MODE_STASH) {
+                prevY[0] = y0acc;
+                prevY[1] = y1acc;
+            } else {
+                u64 zin[2] = {y0acc, y1acc};
+                if ((mode & 3) == MODE_LERP) {
+                    const int k = mode >> 2;
+                    const u64 f = pk(P.mz.f[k], P.mz.f[k]), omf = pk(P.mz.omf[k], P.mz.omf[k]);
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const u64 cur = zin[r];
+                        zin[r] = add2(mul2(prevY[r], omf, K), mul2(cur, f, K), K);
+                        prevY[r] = cur;
+                    }
+                }
+                zout--;  // output z = j + HW completes with this sample
+                optr -= plane_stride;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    u64 prod[HW + 1];
+#pragma unroll
+                    for (int m = 0; m <= HW; m++)
+                        prod[m] = mul2(zin[r], pk(P.taps.t[m], P.taps.t[m]), K);
+#pragma unroll
+                    for (int a = W - 1; a >= 1; a--)
+                        acc[r][a] = add2(prod[a <= HW ? a : 2 * HW - a], acc[r][a - 1], K);
+                    acc[r][0] = add2(prod[0], K.pz, K);
+                }
+                if (zout < sg.zb && zout >= sg.za) {
+                    *reinterpret_cast<u64 *>(optr) = acc[0][W - 1];
+                    *reinterpret_cast<u64 *>(optr + nx) = acc[1][W - 1];
+                }
+            }
+            if (more) store_item(na, nb);  // A is free since S2; visible after the next S1
+        }
+    }
+}
+
+size_t smem_bytes(int hw, int nz)
+{
+    const int NR = TY + 2 * hw;
+    size_t b = (size_t)(NR / 2) * APITCH * sizeof(float2) + (size_t)NR * BPITCH * sizeof(float);
+    b += (size_t)(nz + 2 * hw + 4) * sizeof(short) + (size_t)(nz + 2 * hw + 4);
+    return (b + 15) & ~(size_t)15;
+}
+
+void mirror_table(int n, MirrorTab &m)
+{  // literal f32 evaluation of the right-hand mirror (imutil.c:2376-2380)
+    const int dim_end = n - 1;
+    for (int k = 0; k <= MAXHW; k++) {
+        volatile float c = (float)(dim_end + k);
+        volatile float t = 2.0f * (float)dim_end;
+        t = t - c;
+        t = t - 0.1f;
+        const int lo = (int)t;
+        volatile float f = t - (float)lo;
+        volatile float omf = 1.0f - f;
+        m.lo[k] = lo;
+        m.f[k] = f;
+        m.omf[k] = omf;
+    }
+}
+
+template <int HW>
+int launch(s3d_engine *e, const FusedParams &P, int grid, size_t smem)
+{
+    static bool attr_set[64] = {};
+    if (!attr_set[e->device & 63]) {
+        S3D_CUDA(e, cudaFuncSetAttribute(k_blur_fused<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024));
+        attr_set[e->device & 63] = true;
+    }
+    k_blur_fused<HW><<<grid, NT, smem, e->stream>>>(P);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+}  // namespace
+
+bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps, const float uf[3])
+{
+    const int hw = taps.width / 2;
+    if (nc != 1 || hw < 1 || hw > MAXHW) return false;
+    if (uf[0] != 1.0f || uf[1] != 1.0f || uf[2] != 1.0f) return false;
+    if (nx < TX || ny < TY || nz < 2 * hw + 2 || nx < 2 * hw + 2 || ny < 2 * hw + 2) return false;
+    if ((nx & 3) || nz + 2 * hw + 4 > 32000) return false;  // 16-byte loads; short task table
+    for (int i = 0; i < taps.width; i++)
+        if (taps.t[i] != taps.t[taps.width - 1 - i]) return false;  // Z phase shares products
+    if (smem_bytes(hw, nz) > 200 * 1024) return false;
+    return true;
+}
+
+int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                   const TapSet &taps, const float uf[3])
+{
+    (void)uf;
+    const int hw = taps.width / 2;
+    // ---- work decomposition: columns (overlapping last tile) x balanced z ranges,
+    //      computed once per volume size and cached in the engine -------------------------
+    const SegTab *tab = nullptr;
+    for (const auto &t : e->segtabs)
+        if (t.nx == nx && t.ny == ny && t.nz == nz) tab = &t;
+    if (!tab) {
+        std::vector<int> xs, ys;
+        for (int x = 0; x < nx; x += TX) xs.push_back(std::min(x, nx - TX));
+        for (int y = 0; y < ny; y += TY) ys.push_back(std::min(y, ny - TY));
+        const long ncol = (long)xs.size() * ys.size();
+        const long total = ncol * nz;
+        const int grid = (int)std::min<long>(e->num_sms, std::max<long>(1, total / 16));
+        std::vector<Seg> segs;
+        std::vector<int> start(grid + 1, 0);
+        for (int b = 0; b < grid; b++) {
+            const long s = total * b / grid, t = total * (b + 1) / grid;
+            start[b] = (int)segs.size();
+            long cur = s;
+            while (cur < t) {
+                const long col = cur / nz;
+                const int za = (int)(cur % nz);
+                const int zb = (int)std::min<long>(nz, za + (t - cur));
+                Seg sg;
+                sg.x0 = xs[col % xs.size()];
+                sg.y0 = ys[col / xs.size()];
+                sg.za = za;
+                sg.zb = zb;
+                segs.push_back(sg);
+                cur += zb - za;
+            }
+        }
+        start[grid] = (int)segs.size();
+        const size_t need = segs.size() * sizeof(Seg) + start.size() * sizeof(int);
+        std::vector<unsigned char> host(need);
+        memcpy(host.data(), segs.data(), segs.size() * sizeof(Seg));
+        memcpy(host.data() + segs.size() * sizeof(Seg), start.data(), start.size() * sizeof(int));
+        SegTab nt;
+        nt.nx = nx, nt.ny = ny, nt.nz = nz, nt.grid = grid, nt.nseg = segs.size(), nt.d = nullptr;
+        S3D_CUDA(e, cudaMalloc(&nt.d, need));
+        S3D_CUDA(e, cudaMemcpyAsync(nt.d, host.data(), need, cudaMemcpyHostToDevice, e->stream));
+        S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+        e->segtabs.push_back(nt);
+        tab = &e->segtabs.back();
+    }
+    const int grid = tab->grid;
+    const void *d_tab = tab->d;
+    const size_t nseg = tab->nseg;
+
+    FusedParams P;
+    P.src = src;
+    P.dst = dst;
+    P.nx = nx;
+    P.ny = ny;
+    P.nz = nz;
+    P.segs = reinterpret_cast<const Seg *>(d_tab);
+    P.seg_start = reinterpret_cast<const int *>((const unsigned char *)d_tab + nseg * sizeof(Seg));
+    mirror_table(nx, P.mx);
+    mirror_table(ny, P.my);
+    mirror_table(nz, P.mz);
+    P.taps = taps;
+    P.c_negzero = -0.0f;
+    P.c_one = 1.0f;
+    P.c_zero = 0.0f;
+    const size_t smem = smem_bytes(hw, nz);
+    switch (hw) {
+    case 1: return launch<1>(e, P, grid, smem);
+    case 2: return launch<2>(e, P, grid, smem);
+    case 3: return launch<3>(e, P, grid, smem);
+    case 4: return launch<4>(e, P, grid, smem);
+    case 5: return launch<5>(e, P, grid, smem);
+    case 6: return launch<6>(e, P, grid, smem);
+    case 7: return launch<7>(e, P, grid, smem);
+    case 8: return launch<8>(e, P, grid, smem);
+    }
+    return s3d_fail(e, "fused blur: unsupported width", cudaSuccess, __FILE__, __LINE__);
 }

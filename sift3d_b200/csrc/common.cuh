@@ -47,6 +47,12 @@ struct MeshDev {
     float vert[12][3];  // unit vertex directions (fast-path preselection only)
 };
 
+struct SegTab {  // cached work decomposition of the fused blur for one volume size
+    int nx, ny, nz, grid;
+    void *d;
+    size_t nseg;
+};
+
 struct s3d_engine {
     int device = 0;
     int num_sms = S3D_NUM_SMS_FALLBACK;
@@ -93,6 +99,8 @@ struct s3d_engine {
     int kp_in_cap = 0;
     unsigned char *d_desc = nullptr;
     size_t desc_cap = 0;
+
+    std::vector<SegTab> segtabs;
 
     MeshDev *d_mesh = nullptr;
     bool have_mesh = false;

@@ -168,6 +168,8 @@ void s3d_engine_destroy(s3d_engine *e)
                     e->d_desc, e->d_mesh};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto &t : e->segtabs)
+        if (t.d) cudaFree(t.d);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
