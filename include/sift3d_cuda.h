@@ -138,6 +138,8 @@ int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx,
 int s3d_set_blur_mode(s3d_engine *e, int mode);
 /* Debug/tuning switches: "icos_fast" (1), "blur_mode" (0). */
 int s3d_set_option(s3d_engine *e, const char *name, int value);
+/* Debug: per-CTA {start, end clock, SM id, steps} of the last fused blur (after option "blur_dbg"). */
+int s3d_debug_read(s3d_engine *e, void *host, size_t bytes);
 void *s3d_dev_alloc(s3d_engine *e, size_t bytes);
 void s3d_dev_free(s3d_engine *e, void *p);
 int s3d_memcpy_h2d(s3d_engine *e, void *dev, const void *host, size_t bytes);

@@ -90,6 +90,8 @@ struct FusedParams {
     // fma(a,t,-0) -> mul and fma(p,1,c) -> add and then CONTRACTS the pair into one FFMA2
     // (observed in SASS; -fmad=false does not cover f32x2), which would break bit-exactness.
     float c_negzero, c_one, c_zero;
+    int dbg_flags;   // timing experiments only: 1 = skip right-mirror stores, 2 = skip prev loads, 4 = skip y mirror
+    long long *dbg;  // optional: per CTA {start clock, end clock, smid, steps}
 };
 
 enum { MODE_NORMAL = 0, MODE_STASH = 1, MODE_LERP = 2 };
@@ -116,6 +118,9 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nx = P.nx, ny = P.ny, nz = P.nz;
+    long long dbg_t0 = 0;
+    int dbg_steps = 0;
+    if (P.dbg && tid == 0) dbg_t0 = clock64();
     const size_t plane_stride = (size_t)nx * ny;
     Consts K;
     K.nz = pk(P.c_negzero, P.c_negzero);
@@ -129,7 +134,6 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
         const Seg sg = P.segs[si];
         const int x0 = sg.x0, y0 = sg.y0;
         const bool ybound = (y0 - HW < 0) || (y0 + TY + HW > ny - 1);
-        const bool xbound = (x0 - HW < 0) || (x0 + TX + HW > nx - 1);
         // ---- task list: samples j = zb-1+HW .. za-HW of the extended z line --------------
         __syncthreads();
         int ntask;
@@ -163,21 +167,38 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
         const int frp = tid / AWQ, fq = tid - frp * AWQ;
         const int fy = y0 - HW + 2 * frp;        // global row of the pair's first row
         const int fx = x0 - HWA + 4 * fq;        // global column of the group's first column
-        const bool cols_in = fx >= 0 && fx + 3 <= nx - 1;   // group inside the volume (x0, nx, HWA % 4 == 0)
+        const bool cols_in = fx >= 0 && fx + 3 <= nx - 1;  // group inside the volume
         const bool row0_ok = fill_thread && cols_in && fy >= 0 && fy < ny;
         const bool row1_ok = fill_thread && cols_in && fy + 1 >= 0 && fy + 1 < ny;
+        // x mirror samples are written by the thread that owns their SOURCE columns, from the
+        // registers it loaded anyway (no extra pass, barrier or exposed latency):
+        //   x < 0      : column -x is a copy of column x            (1 <= x <= HW)
+        //   x >= nx-1  : omf*col[lo] + f*col[lo+1], written by the owner of col lo+1; col lo is
+        //                its previous column (one extra scalar load when lo+1 starts a group)
+        const bool xedge = (x0 - HW < 0) || (x0 + TX + HW > nx - 1);  // block-uniform
+        int lt[4], rk[4];
+        bool need_prev = false;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int x = fx + c;
+            lt[c] = (cols_in && x >= 1 && x <= HW && x0 - HW < 0) ? (-x - (x0 - HWA)) : -1;
+            const int k = nx - 1 - x;  // column x is `hi` of right-mirror sample k
+            const bool r = cols_in && k >= 0 && k <= HW && x >= 1 && nx - 1 + k < x0 + TX + HW;
+            rk[c] = r ? k : -1;
+            if (c == 0 && r) need_prev = true;
+        }
         const float *g0 = P.src + (size_t)(row0_ok ? fy : 0) * nx;
         const float *g1 = P.src + (size_t)(row1_ok ? fy + 1 : 0) * nx;
         float2 *fdst = A + frp * APITCH + 4 * fq;
 
-        // one row of the group: a single aligned 16-byte load; groups that lie outside
-        // [0, nx) are skipped and synthesised in shared memory by the X-mirror patch
+        // one row of the group: a single aligned 16-byte load (groups outside the volume are
+        // skipped: their columns are mirror samples, synthesised at store time -- see below)
         auto load4 = [&](const float *row, bool ok) -> float4 {
             if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
             return __ldg(reinterpret_cast<const float4 *>(row + fx));
         };
-        auto store_item = [&](const float4 a, const float4 b) {
-            if (!fill_thread) return;
+        auto store_item = [&](const float4 a, const float4 b, const float pa, const float pb) {
+            if (!fill_thread || !cols_in) return;  // groups outside the volume hold mirror samples
             const float4 lo4 = make_float4(a.x, b.x, a.y, b.y), hi4 = make_float4(a.z, b.z, a.w, b.w);
             float4 *d = reinterpret_cast<float4 *>(fdst);
             if (swap_st) {
@@ -187,6 +208,25 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
                 d[0] = lo4;
                 d[1] = hi4;
             }
+            if (xedge) {
+                float2 *rowp = A + frp * APITCH;
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (lt[c] >= 0) rowp[lt[c]] = make_float2(av[c], bv[c]);
+                    if (rk[c] >= 0 && !(P.dbg_flags & 1)) {
+                        const int k = rk[c];
+                        const float om = P.mx.omf[k], ff = P.mx.f[k];
+                        const float p0 = c ? av[c ? c - 1 : 0] : pa, p1 = c ? bv[c ? c - 1 : 0] : pb;
+                        rowp[nx - 1 + k - (x0 - HWA)] =
+                            make_float2(__fadd_rn(__fmul_rn(om, p0), __fmul_rn(ff, av[c])),
+                                        __fadd_rn(__fmul_rn(om, p1), __fmul_rn(ff, bv[c])));
+                    }
+                }
+            }
+        };
+        auto load_prev = [&](const float *row, bool ok) -> float {
+            return (need_prev && ok && !(P.dbg_flags & 2)) ? __ldg(row + fx - 1) : 0.f;
         };
 
         u64 acc[2][W];  // Z-phase partial sums by age, for the thread's two rows
@@ -196,46 +236,31 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
         prevY[0] = prevY[1] = K.pz;
         __syncthreads();  // task table visible
 
-        {   // first plane
+        // Register-staged prefetch.  Narrow filters do too little arithmetic per plane to hide a
+        // DRAM round trip behind one step, so for HW <= 4 (where registers allow) the loads run
+        // TWO planes ahead: (qa, qb) holds plane t+1 and is stored at the end of step t, (na, nb)
+        // receives plane t+2.
+        constexpr bool PF2 = HW <= 4;
+        float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+        float qpa = 0.f, qpb = 0.f;
+        {   // first plane (and, with PF2, the second)
             const size_t off = (size_t)task_plane[0] * plane_stride;
-            store_item(load4(g0 + off, row0_ok), load4(g1 + off, row1_ok));
+            store_item(load4(g0 + off, row0_ok), load4(g1 + off, row1_ok), load_prev(g0 + off, row0_ok),
+                       load_prev(g1 + off, row1_ok));
+            if (PF2 && ntask > 1) {
+                const size_t off1 = (size_t)task_plane[1] * plane_stride;
+                qa = load4(g0 + off1, row0_ok);
+                qb = load4(g1 + off1, row1_ok);
+                qpa = load_prev(g0 + off1, row0_ok);
+                qpb = load_prev(g1 + off1, row1_ok);
+            }
         }
         // output pointer of z = zb + 2HW (moved down one plane per z step)
         float *optr = P.dst + ((size_t)(sg.zb + 2 * HW) * ny + (y0 + 2 * warp)) * nx + x0 + 2 * lane;
         int zout = sg.zb + 2 * HW;
+        dbg_steps += ntask;
         for (int t = 0; t < ntask; t++) {
             __syncthreads();  // S1: A holds plane t; B free
-
-            if (xbound) {  // mirror columns of A outside [0, nx-1) (block-uniform branch)
-                const int nl = x0 - HW < 0 ? HW - x0 : 0;                       // columns x < 0
-                const int nrt = x0 + TX + HW > nx - 1 ? x0 + TX + HW - (nx - 1) : 0;  // x >= nx-1
-                const int ncol = nl + nrt;
-                float *Af = reinterpret_cast<float *>(A);
-                float vals[3];
-                int idx[3], cnt = 0;
-                for (int e = tid; e < NR * ncol; e += NT) {
-                    const int r = e / ncol, c = e - r * ncol;
-                    const int base = ((r >> 1) * APITCH) * 2 + (r & 1);
-                    int xa;
-                    float v;
-                    if (c < nl) {  // x = c - HW ... : global x = x0 - HW + c < 0
-                        const int x = x0 - HW + c;
-                        xa = x - (x0 - HWA);
-                        v = Af[base + 2 * (-x - (x0 - HWA))];
-                    } else {
-                        const int k = c - nl;  // x = nx-1+k
-                        xa = nx - 1 + k - (x0 - HWA);
-                        const int lo = P.mx.lo[k] - (x0 - HWA);
-                        v = __fadd_rn(__fmul_rn(P.mx.omf[k], Af[base + 2 * lo]),
-                                      __fmul_rn(P.mx.f[k], Af[base + 2 * (lo + 1)]));
-                    }
-                    idx[cnt] = base + 2 * xa;
-                    vals[cnt++] = v;
-                }
-                __syncthreads();
-                for (int q = 0; q < cnt; q++) Af[idx[q]] = vals[q];
-                __syncthreads();
-            }
 
             // ---- X phase: warp = run of 4 outputs, lane = row pair --------------------------
             if (lane < NRP) {
@@ -270,41 +295,56 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
                     *reinterpret_cast<float4 *>(brow) = r0;
                     *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
                 }
+                if (ybound && !(P.dbg_flags & 4)) {
+                    // rows outside [0, ny-1) are synthesised here, from registers, by the thread
+                    // that owns their source rows (no extra pass, no extra barrier):
+                    //   y < 0      : copy of row -y
+                    //   y >= ny-1  : omf*row[lo] + f*row[lo+1]; the thread owning row lo+1 writes
+                    //                it, taking row lo from its own pair or from the lane below
+                    const int ya = y0 - HW + 2 * lane;  // global y of the pair's first row
+                    constexpr unsigned xmask = NRP >= 32 ? 0xffffffffu : ((1u << NRP) - 1u);
+                    const float4 below = make_float4(__shfl_up_sync(xmask, r1.x, 1),
+                                                     __shfl_up_sync(xmask, r1.y, 1),
+                                                     __shfl_up_sync(xmask, r1.z, 1),
+                                                     __shfl_up_sync(xmask, r1.w, 1));
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int y = ya + h;
+                        const float4 cur = h ? r1 : r0;
+                        const float4 prv = h ? r0 : below;  // row y-1
+                        if (y >= 1 && y <= HW && -y >= y0 - HW)  // top mirror target row -y
+                            *reinterpret_cast<float4 *>(B + (-y - (y0 - HW)) * BPITCH + 4 * warp) = cur;
+                        const int k = ny - 1 - y;  // this row is `hi` of mirror sample k
+                        if (k >= 0 && k <= HW && y >= 1 && ny - 1 + k < y0 + TY + HW) {
+                            const float om = P.my.omf[k], ff = P.my.f[k];
+                            float4 v;
+                            v.x = __fadd_rn(__fmul_rn(om, prv.x), __fmul_rn(ff, cur.x));
+                            v.y = __fadd_rn(__fmul_rn(om, prv.y), __fmul_rn(ff, cur.y));
+                            v.z = __fadd_rn(__fmul_rn(om, prv.z), __fmul_rn(ff, cur.z));
+                            v.w = __fadd_rn(__fmul_rn(om, prv.w), __fmul_rn(ff, cur.w));
+                            // k = 0 overwrites row ny-1 itself: done after the plain store above
+                            *reinterpret_cast<float4 *>(B + (ny - 1 + k - (y0 - HW)) * BPITCH + 4 * warp) = v;
+                        }
+                    }
+                }
             }
             __syncthreads();  // S2: B complete, A free
 
-            // prefetch the next plane into registers; stored to A after the Z phase
+            // prefetch into registers; stored to A after the Z phase
             float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+            float npa = 0.f, npb = 0.f;
             const bool more = t + 1 < ntask;
-            if (more) {
-                const size_t off = (size_t)task_plane[t + 1] * plane_stride;
-                na = load4(g0 + off, row0_ok);
-                nb = load4(g1 + off, row1_ok);
-            }
-
-            if (ybound) {  // mirror rows of B outside [0, ny-1) (block-uniform branch)
-                const int nt_ = y0 - HW < 0 ? HW - y0 : 0;                          // rows y < 0
-                const int nb_ = y0 + TY + HW > ny - 1 ? y0 + TY + HW - (ny - 1) : 0;  // y >= ny-1
-                float vals[3];
-                int idx[3], cnt = 0;
-                for (int e = tid; e < (nt_ + nb_) * TX; e += NT) {
-                    const int rr = e / TX, x = e - rr * TX;
-                    if (rr < nt_) {  // tile row rr <-> y = y0 - HW + rr < 0; source row of -y
-                        const int y = y0 - HW + rr;
-                        idx[cnt] = rr * BPITCH + x;
-                        vals[cnt++] = B[(rr - 2 * y) * BPITCH + x];
-                    } else {
-                        const int k = rr - nt_;  // y = ny-1+k
-                        const int r = ny - 1 + k - (y0 - HW);
-                        const int rl = P.my.lo[k] - (y0 - HW);
-                        idx[cnt] = r * BPITCH + x;
-                        vals[cnt++] = __fadd_rn(__fmul_rn(P.my.omf[k], B[rl * BPITCH + x]),
-                                                __fmul_rn(P.my.f[k], B[(rl + 1) * BPITCH + x]));
+            {
+                const int tp = PF2 ? t + 2 : t + 1;
+                if (tp < ntask) {
+                    const size_t off = (size_t)task_plane[tp] * plane_stride;
+                    na = load4(g0 + off, row0_ok);
+                    nb = load4(g1 + off, row1_ok);
+                    if (xedge) {
+                        npa = load_prev(g0 + off, row0_ok);
+                        npb = load_prev(g1 + off, row1_ok);
                     }
                 }
-                __syncthreads();
-                for (int q = 0; q < cnt; q++) B[idx[q]] = vals[q];
-                __syncthreads();
             }
 
             // ---- Y phase: rows y = 2*warp, 2*warp+1; x pair = lane ---------------------------
@@ -354,8 +394,21 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
                     *reinterpret_cast<u64 *>(optr + nx) = acc[1][W - 1];
                 }
             }
-            if (more) store_item(na, nb);  // A is free since S2; visible after the next S1
+            if (PF2) {
+                if (more) store_item(qa, qb, qpa, qpb);
+                qa = na, qb = nb, qpa = npa, qpb = npb;
+            } else if (more) {
+                store_item(na, nb, npa, npb);
+            }  // A is free since S2; visible after the next S1
         }
+    }
+    if (P.dbg && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.dbg[4 * blockIdx.x + 0] = dbg_t0;
+        P.dbg[4 * blockIdx.x + 1] = clock64();
+        P.dbg[4 * blockIdx.x + 2] = smid;
+        P.dbg[4 * blockIdx.x + 3] = dbg_steps;
     }
 }
 
@@ -430,23 +483,50 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
         const long ncol = (long)xs.size() * ys.size();
         const long total = ncol * nz;
         const int grid = (int)std::min<long>(e->num_sms, std::max<long>(1, total / 16));
+        // Edge columns cost more per plane (mirror samples are synthesised by a few threads on the
+        // critical path of every step); measured on B200 (tools/blur_dbg.py, cycles/step relative
+        // to an interior column): left 1.11, right 1.30, top 1.06, bottom 1.19.  The z ranges are
+        // balanced by cost so that all persistent CTAs finish together.
+        std::vector<double> wcol(ncol);
+        double wsum = 0;
+        for (long c = 0; c < ncol; c++) {
+            const int x0 = xs[c % xs.size()], y0 = ys[c / xs.size()];
+            double w = 1.0;
+            if (x0 - hw < 0) w *= 1.11;
+            if (x0 + TX + hw > nx - 1) w *= 1.30;
+            if (y0 - hw < 0) w *= 1.06;
+            if (y0 + TY + hw > ny - 1) w *= 1.19;
+            wcol[c] = w;
+            wsum += w * nz;
+        }
         std::vector<Seg> segs;
         std::vector<int> start(grid + 1, 0);
-        for (int b = 0; b < grid; b++) {
-            const long s = total * b / grid, t = total * (b + 1) / grid;
-            start[b] = (int)segs.size();
-            long cur = s;
-            while (cur < t) {
-                const long col = cur / nz;
-                const int za = (int)(cur % nz);
-                const int zb = (int)std::min<long>(nz, za + (t - cur));
-                Seg sg;
-                sg.x0 = xs[col % xs.size()];
-                sg.y0 = ys[col / xs.size()];
-                sg.za = za;
-                sg.zb = zb;
-                segs.push_back(sg);
-                cur += zb - za;
+        {
+            const double quota = wsum / grid;
+            long col = 0;
+            int z = 0;
+            for (int b = 0; b < grid; b++) {
+                start[b] = (int)segs.size();
+                double need = quota;
+                while (col < ncol && (need > 1e-9 || b == grid - 1)) {
+                    const double per = wcol[col] + 2.0 * hw * wcol[col] / std::max(nz, 1) * 0;  // halo ignored
+                    int take = (b == grid - 1) ? nz - z : (int)std::min<double>(nz - z, std::ceil(need / per - 1e-9));
+                    if (take <= 0) break;
+                    // avoid leaving a sliver shorter than the halo at the end of a column
+                    if (nz - (z + take) > 0 && nz - (z + take) < 2 * hw && b != grid - 1) take = nz - z;
+                    Seg sg;
+                    sg.x0 = xs[col % xs.size()];
+                    sg.y0 = ys[col / xs.size()];
+                    sg.za = z;
+                    sg.zb = z + take;
+                    segs.push_back(sg);
+                    need -= take * per;
+                    z += take;
+                    if (z >= nz) {
+                        z = 0;
+                        col++;
+                    }
+                }
             }
         }
         start[grid] = (int)segs.size();
@@ -481,6 +561,8 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
     P.c_negzero = -0.0f;
     P.c_one = 1.0f;
     P.c_zero = 0.0f;
+    P.dbg = e->d_blur_dbg;
+    P.dbg_flags = e->opt_blur_flags;
     const size_t smem = smem_bytes(hw, nz);
     switch (hw) {
     case 1: return launch<1>(e, P, grid, smem);

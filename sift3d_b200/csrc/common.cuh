@@ -62,6 +62,8 @@ struct s3d_engine {
     long long launches = 0;
     int blur_mode = 0;
     int opt_icos_fast = 1;
+    int opt_desc_v1 = 0;
+    int opt_blur_flags = 0;  // timing experiments only (results wrong when non-zero)
 
     // pyramid
     int noct = 0, K = 0, nlev_g = 0, nlev_d = 0;
@@ -101,6 +103,7 @@ struct s3d_engine {
     size_t desc_cap = 0;
 
     std::vector<SegTab> segtabs;
+    long long *d_blur_dbg = nullptr;  // debug: per-CTA clocks of the last fused blur
 
     MeshDev *d_mesh = nullptr;
     bool have_mesh = false;

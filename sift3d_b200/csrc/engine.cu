@@ -165,7 +165,7 @@ void s3d_engine_destroy(s3d_engine *e)
     free_pyramid(e);
     void *ptrs[] = {e->im,    e->scratch[0], e->scratch[1], e->d_cand,  e->d_mask, e->d_blockcnt,
                     e->d_counter, e->d_kp_all, e->d_ok,       e->d_pos,   e->d_kp,   e->d_kp_in,
-                    e->d_desc, e->d_mesh};
+                    e->d_desc, e->d_mesh, e->d_blur_dbg};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &t : e->segtabs)
@@ -204,6 +204,15 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
 {
     if (!strcmp(name, "icos_fast")) e->opt_icos_fast = value;
     else if (!strcmp(name, "blur_mode")) e->blur_mode = value;
+    else if (!strcmp(name, "desc_v1")) e->opt_desc_v1 = value;
+    else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
+    else if (!strcmp(name, "blur_dbg")) {
+        DeviceGuard guard(e->device);
+        if (value && !e->d_blur_dbg) {
+            S3D_CUDA(e, cudaMalloc(&e->d_blur_dbg, 4 * 1024 * sizeof(long long)));
+            S3D_CUDA(e, cudaMemset(e->d_blur_dbg, 0, 4 * 1024 * sizeof(long long)));
+        }
+    }
     else return s3d_fail(e, "s3d_set_option: unknown option", cudaSuccess, __FILE__, __LINE__);
     return 0;
 }
@@ -682,6 +691,15 @@ int s3d_pyramid_copy(s3d_engine *dst, const s3d_engine *src)
     dst->first_taps = src->first_taps;
     dst->oct_taps = src->oct_taps;
     S3D_CUDA(dst, cudaStreamSynchronize(dst->stream));
+    return 0;
+}
+
+int s3d_debug_read(s3d_engine *e, void *host, size_t bytes)
+{
+    DeviceGuard guard(e->device);
+    if (!e->d_blur_dbg) return -1;
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    S3D_CUDA(e, cudaMemcpy(host, e->d_blur_dbg, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 

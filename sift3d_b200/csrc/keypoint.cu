@@ -28,6 +28,9 @@ __device__ __forceinline__ float dot3(float a, float b, float c, float d, float 
 
 #define K_BARY_EPS ((double)FLT_EPSILON * 1E1)
 
+// unit centroid directions of the 20 faces: uniform (unrolled) access -> constant bank operands
+__constant__ float c_vmid[20][3];
+
 // cart2bary (sift.c:335-394) with the per-face constants hoisted.
 __device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], float bary[3])
 {
@@ -51,29 +54,40 @@ __device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], 
 // is the containing face; if its barycentrics are all comfortably positive no
 // other face can pass (faces only overlap within bary_eps of shared edges), so
 // it is also the first.  Otherwise fall back to the literal in-order loop.
-__device__ __forceinline__ int icos_bin(const MeshDev *__restrict__ M, const float g[3],
+__device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, const float g[3],
                                         float bary[3], const bool fast = true)
 {
     const float n2 = fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2]));
     if ((double)n2 < K_BARY_EPS) return -1;
-    // preselect by centroid direction (any monotone proxy is fine: it is verified)
-    int best = 0;
-    float bd = -FLT_MAX;
+    if (fast) {
+        // preselect by centroid direction (any proxy is fine: the choice is verified)
+        int best = 0;
+        float bd = -FLT_MAX;
 #pragma unroll
-    for (int i = 0; i < 20; i++) {
-        const float d = g[0] * M->f[i].vmid[0] + g[1] * M->f[i].vmid[1] + g[2] * M->f[i].vmid[2];
-        if (d > bd) {
-            bd = d;
-            best = i;
+        for (int i = 0; i < 20; i++) {
+            const float d = g[0] * c_vmid[i][0] + g[1] * c_vmid[i][1] + g[2] * c_vmid[i][2];
+            if (d > bd) {
+                bd = d;
+                best = i;
+            }
         }
+        const float margin = 1e-4f;
+        if (face_test(F[best], g, bary) && bary[0] > margin && bary[1] > margin &&
+            bary[2] > margin)
+            return best;
     }
-    const float margin = 1e-4f;
-    if (fast && face_test(M->f[best], g, bary) && bary[0] > margin && bary[1] > margin &&
-        bary[2] > margin)
-        return best;
     for (int i = 0; i < 20; i++)
-        if (face_test(M->f[i], g, bary)) return i;
+        if (face_test(F[i], g, bary)) return i;
     return -1;
+}
+
+// stage the per-face constants in shared memory (divergent indexing by face)
+__device__ __forceinline__ void load_faces(FaceConst *s_face, const MeshDev *__restrict__ M)
+{
+    const int nw = 20 * (int)(sizeof(FaceConst) / 4);
+    const unsigned *src = reinterpret_cast<const unsigned *>(M->f);
+    unsigned *dst = reinterpret_cast<unsigned *>(s_face);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
 // cyclic Jacobi, f64, ascending eigenvalues, eigenvectors in the columns of Q
@@ -165,6 +179,43 @@ __device__ __forceinline__ void sphere_bounds_f(float c, float rad, float uf, in
     hi = (int)fminf(ceilf(fa(c, __fdiv_rn(rad, uf))), (float)(n - 2));
 }
 
+// expf exactly as glibc >= 2.27 computes it (sysdeps/ieee754/flt-32/e_expf.c: N = 32 table,
+// degree-3 polynomial in f64, result narrowed to f32), for |x| < 88.  Checked on the host
+// against libm's expf: 0 mismatches in 2e7 random arguments in [-2.2, 0], for both the
+// FMA and the non-FMA evaluation order (tools/expf_check.c).  A merely "correctly rounded"
+// exp differs from glibc in 0.06 % of the calls, CUDA's 2-ulp expf in far more; a 1-ulp
+// change of a window weight can flip the icosahedron face of a gradient that sits within
+// bary_eps of an edge, so the weights are reproduced bit for bit instead.
+__constant__ unsigned long long c_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+
+__device__ __forceinline__ float expf_glibc(float x, const unsigned long long *tab /* shared */)
+{
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32,
+                 C2 = 0x1.62e42ff0c52d6p-1 / 32;
+    const double z = __dmul_rn(InvLn2N, (double)x);
+    double kd = __dadd_rn(z, SHIFT);
+    const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, SHIFT);
+    const double r = __dsub_rn(z, kd);
+    const unsigned long long t = tab[ki & 31] + (ki << 47);
+    const double sc = __longlong_as_double((long long)t);
+    const double zz = __fma_rn(C0, r, C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(C2, r, 1.0);
+    y = __fma_rn(zz, r2, y);
+    y = __dmul_rn(y, sc);
+    return (float)y;
+}
+
 // ---------------------------------------------------------------- orientation
 // One thread per candidate, accumulating in the reference's raster order so the
 // f32 window gradient and the f64 structure tensor see the same rounding
@@ -175,6 +226,9 @@ __global__ void __launch_bounds__(128)
     k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
              double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out)
 {
+    __shared__ unsigned long long s_tab[32];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const s3d_keypoint c = kps[i];
@@ -210,9 +264,9 @@ __global__ void __launch_bounds__(128)
                 const float sq = fa(fa(fm(dx, dx), dy2), dz2);
                 if ((double)sq > r2) continue;
                 // weight = expf(-0.5 * sq_dist / (sigma * sigma)), sift.c:1401: f64
-                // argument narrowed to f32, then a correctly rounded f32 exp
+                // argument narrowed to f32, then glibc's expf
                 const float arg = (float)__ddiv_rn(__dmul_rn(-0.5, (double)sq), s2);
-                const float w = (float)exp((double)arg);
+                const float w = expf_glibc(arg, s_tab);
                 const float *p = row + x;
                 float gx = fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1)));
                 float gy = fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys)));
@@ -360,8 +414,12 @@ __global__ void __launch_bounds__(DESC_THREADS)
     __shared__ float hist[S3D_DESC_NUMEL];
     __shared__ double s_red[DESC_THREADS / 32];
     __shared__ float s_norm_inv;
+    __shared__ unsigned long long s_tab[32];
+    __shared__ FaceConst s_face[20];
     const int ki = blockIdx.x;
     if (ki >= n) return;
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+    load_faces(s_face, M);
     const s3d_keypoint kp = kps[ki];
     const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
     const float *__restrict__ im = T.ptrs[lv];
@@ -418,12 +476,8 @@ __global__ void __launch_bounds__(DESC_THREADS)
         g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
         g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
         g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
-        // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument.  glibc's expf is
-        // correctly rounded in all but ~0.1 % of calls; CUDA's expf is only 2-ulp accurate, and a
-        // 1-ulp change of the weight can flip the icosahedron face of a gradient that sits within
-        // bary_eps of an edge (observed: one voxel in ~100 keypoints -> 2e-4 descriptor error).  A
-        // f64 exp rounded to f32 reproduces the correctly rounded value.
-        const float w = (float)exp((double)__fdiv_rn(fm(-0.5f, sq), s2));
+        // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument, glibc's expf
+        const float w = expf_glibc(__fdiv_rn(fm(-0.5f, sq), s2), s_tab);
         g[0] = fm(g[0], w);
         g[1] = fm(g[1], w);
         g[2] = fm(g[2], w);
@@ -432,7 +486,7 @@ __global__ void __launch_bounds__(DESC_THREADS)
         for (int a = 0; a < 3; a++)
             gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
         float bary[3];
-        const int bin = icos_bin(M, gr, bary, icos_fast != 0);
+        const int bin = icos_bin(s_face, gr, bary, icos_fast != 0);
         if (bin < 0) continue;
         const float mag = __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
         float dv[3];
@@ -442,7 +496,7 @@ __global__ void __launch_bounds__(DESC_THREADS)
             dv[a] = fs(vb[a], floorf(vb[a]));
             ib[a] = (int)vb[a];
         }
-        const int i0 = M->f[bin].idx[0], i1 = M->f[bin].idx[1], i2 = M->f[bin].idx[2];
+        const int i0 = s_face[bin].idx[0], i1 = s_face[bin].idx[1], i2 = s_face[bin].idx[2];
 #pragma unroll
         for (int dx = 0; dx < 2; dx++)
 #pragma unroll
@@ -502,6 +556,243 @@ __global__ void __launch_bounds__(DESC_THREADS)
     }
 }
 
+// Descriptor, version 2 (the default).  Per keypoint CTA:
+//   phase A  warps scan the rows of the window's bounding box, pruned to the sphere's x
+//            extent, apply the reference's exact sphere / descriptor-cube tests and append the
+//            surviving voxels to a shared list (ballot + one counter atomic per warp);
+//   phase B  the list is consumed with a strided assignment (neighbouring lanes take voxels
+//            far apart, i.e. in different spatial cells) and every lane does the full
+//            per-voxel work: gradient, glibc-exact window weight, rotation, icosahedron bin,
+//            24 histogram updates.
+// The histogram is 64-bit FIXED POINT (2^-32 units, lo/hi words updated with native 32-bit
+// shared atomics and an explicit carry): integer addition is associative, so the descriptor is
+// bit-reproducible from run to run, and same-address conflicts cost no retry loops.
+#define DESC2_THREADS 256
+#define DESC2_LIST 9216  // entries; split into one segment per warp
+
+__global__ void __launch_bounds__(DESC2_THREADS)
+    k_descriptor2(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
+                  const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
+{
+    __shared__ unsigned list[DESC2_LIST];
+    __shared__ unsigned h_lo[S3D_DESC_NUMEL + 1];  // +1: dummy slot for out-of-grid corners
+    __shared__ int h_hi[S3D_DESC_NUMEL + 1];
+    float *hist = reinterpret_cast<float *>(list);  // the list is dead when hist is written
+    __shared__ unsigned long long s_tab[32];
+    __shared__ double s_red[DESC2_THREADS / 32];
+    __shared__ FaceConst s_face[20];
+    __shared__ float s_norm_inv;
+    __shared__ int s_segcount[DESC2_THREADS / 32];
+    const int ki = blockIdx.x;
+    if (ki >= n) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const s3d_keypoint kp = kps[ki];
+    const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
+    const float *__restrict__ im = T.ptrs[lv];
+    const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
+    const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
+    const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
+    const float sigma = (float)__dmul_rn(kp.sd, 7.071067812);  // sift.c:1845-1850
+    const float win_radius = (float)__dmul_rn(2.0, (double)sigma);
+    const float half = (float)__ddiv_rn((double)win_radius, sqrt(2.0));
+    const float desc_width = fm(2.0f, half);
+    const float hist_width = __fdiv_rn(desc_width, 4.0f);
+    const float bin_fctr = __fdiv_rn(1.0f, hist_width);
+    const float r2 = fm(win_radius, win_radius);
+    const float s2 = fm(sigma, sigma);
+    int x0, x1, y0, y1, z0, z1;
+    sphere_bounds_f(kp.x, win_radius, uxf, nx, x0, x1);
+    sphere_bounds_f(kp.y, win_radius, uyf, ny, y0, y1);
+    sphere_bounds_f(kp.z, win_radius, uzf, nz, z0, z1);
+    float Rt[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Rt[3 * i + j] = kp.R[3 * j + i];
+
+    for (int i = tid; i < S3D_DESC_NUMEL + 1; i += DESC2_THREADS) {
+        h_lo[i] = 0u;
+        h_hi[i] = 0;
+    }
+    if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
+    load_faces(s_face, M);
+    __syncthreads();
+
+    const int bx = max(x1 - x0 + 1, 0), by = max(y1 - y0 + 1, 0), bz = max(z1 - z0 + 1, 0);
+    const int nrows = by * bz;
+    const int rows_per_batch = 0;
+    const int bx_safe = max(bx, 1);
+    const size_t ys = nx, zs = (size_t)nx * ny;
+
+    // spatial-bin coordinates of a voxel; false if outside the sphere or the descriptor cube
+    auto geom = [&](int x, int y, int z, float &sq, float vb[3]) -> bool {
+        const float vx = fm(fs((float)x, kp.x), uxf);
+        const float vy = fm(fs((float)y, kp.y), uyf);
+        const float vz = fm(fs((float)z, kp.z), uzf);
+        sq = fa(fa(fm(vx, vx), fm(vy, vy)), fm(vz, vz));
+        if (sq > r2) return false;
+        bool inside = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float vk = dot3(Rt[3 * a], vx, Rt[3 * a + 1], vy, Rt[3 * a + 2], vz);
+            vb[a] = fm(fa(vk, half), bin_fctr);
+            inside = inside && !(vb[a] < 0.0f || vb[a] >= 4.0f);
+        }
+        return inside;
+    };
+
+    // rows of a batch are split statically among the warps and every warp appends to its own
+    // list segment, so the list is the same on every run
+    constexpr int NWARP = DESC2_THREADS / 32;
+    constexpr int SEGCAP = DESC2_LIST / NWARP;
+    const int rows_per_warp = max(SEGCAP / bx_safe, 1);
+    const int rows_per_batch2 = rows_per_warp * NWARP;
+    (void)rows_per_batch;
+    for (int rb = 0; rb < nrows && bx > 0; rb += rows_per_batch2) {
+        // ---------------- phase A: scan + compact ------------------------------------------
+        int mycount = 0;  // entries in this warp's segment (warp-uniform)
+        unsigned *seg = list + warp * SEGCAP;
+        for (int i = 0; i < rows_per_warp; i++) {
+            const int row = rb + warp * rows_per_warp + i;
+            if (row >= nrows) break;
+            const int y = y0 + row % by, z = z0 + row / by;
+            const float dy = fm(fs((float)y, kp.y), uyf), dz = fm(fs((float)z, kp.z), uzf);
+            const float rem = r2 - (dy * dy + dz * dz);
+            if (rem < -1e-3f * r2) continue;  // whole row outside the sphere (conservative)
+            const float hx = sqrtf(fmaxf(rem, 0.0f)) * iux + 1.5f;
+            const int xa = max(x0, (int)floorf(kp.x - hx)), xb = min(x1, (int)ceilf(kp.x + hx));
+            for (int xs = xa; xs <= xb; xs += 32) {
+                const int x = xs + lane;
+                float sq, vb[3];
+                const bool ok = x <= xb && geom(x, y, z, sq, vb);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok)
+                    seg[mycount + __popc(m & ((1u << lane) - 1u))] =
+                        (unsigned)(x - x0) | ((unsigned)(y - y0) << 10) | ((unsigned)(z - z0) << 20);
+                mycount += __popc(m);
+            }
+        }
+        if (lane == 0) s_segcount[warp] = mycount;
+        __syncthreads();
+        int pre[NWARP + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) pre[w + 1] = pre[w] + s_segcount[w];
+        const int count = pre[NWARP];
+        // ---------------- phase B: per-voxel work ---------------------------------------------
+        // thread t owns the contiguous virtual range [t*L, t*L+L): consecutive voxels of a
+        // thread are x-neighbours (long list locality), the lanes of a warp are L apart
+        const int L = (count + DESC2_THREADS - 1) / DESC2_THREADS;
+        const int tperm = lane * NWARP + warp;  // neighbouring lanes far apart in the list
+        for (int k = 0; k < L; k++) {
+            const int e = tperm * L + k;
+            if (e >= count) break;
+            int w = 0;
+#pragma unroll
+            for (int q = 1; q < NWARP; q++) w += (e >= pre[q]) ? 1 : 0;
+            const unsigned code = list[w * SEGCAP + (e - pre[w])];
+            const int x = x0 + (int)(code & 1023u), y = y0 + (int)((code >> 10) & 1023u),
+                      z = z0 + (int)(code >> 20);
+            float sq, vb[3];
+            geom(x, y, z, sq, vb);
+            const float *p = im + x + (size_t)y * ys + (size_t)z * zs;
+            float g[3];
+            g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+            g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+            g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+            // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument
+            const float wgt_win = expf_glibc(__fdiv_rn(fm(-0.5f, sq), s2), s_tab);
+            g[0] = fm(g[0], wgt_win);
+            g[1] = fm(g[1], wgt_win);
+            g[2] = fm(g[2], wgt_win);
+            float gr[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+                gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
+            float bary[3];
+            const int bin = icos_bin(s_face, gr, bary, icos_fast != 0);
+            if (bin < 0) continue;
+            const float mag =
+                __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
+            float dv[3];
+            int ib[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                dv[a] = fs(vb[a], floorf(vb[a]));
+                ib[a] = (int)vb[a];
+            }
+            const int i0 = s_face[bin].idx[0], i1 = s_face[bin].idx[1], i2 = s_face[bin].idx[2];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int cx = ib[0] + (c >> 2), cy = ib[1] + ((c >> 1) & 1), cz = ib[2] + (c & 1);
+                const bool in = cx < 4 && cy < 4 && cz < 4;  // corners outside the grid add nothing
+                const int cell = 12 * (cx + 4 * cy + 16 * cz);
+                const float wgt = fm(fm((c >> 2) ? dv[0] : fs(1.0f, dv[0]),
+                                        ((c >> 1) & 1) ? dv[1] : fs(1.0f, dv[1])),
+                                     (c & 1) ? dv[2] : fs(1.0f, dv[2]));
+                const float mw = fm(mag, wgt);  // (mag * weight) * bary_j, sift.c:1763-1765
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const int b = cell + (j == 0 ? i0 : (j == 1 ? i1 : i2));
+                    const long long q = __float2ll_rn(fm(fm(mw, bary[j]), 4294967296.0f));
+                    const unsigned ql = (unsigned)q;
+                    if (in) {
+                        const unsigned old = atomicAdd(&h_lo[b], ql);
+                        const int qh = (int)(q >> 32) + ((old + ql) < old ? 1 : 0);
+                        if (qh) atomicAdd(&h_hi[b], qh);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // fixed point -> f32
+    for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) {
+        const long long v = ((long long)h_hi[i] << 32) | (long long)h_lo[i];
+        hist[i] = (float)((double)v * (1.0 / 4294967296.0));
+    }
+    __syncthreads();
+
+    // normalize_desc (sift.c:1794-1821), truncate (sift.c:1909-1915), normalize again
+    const float trunc = (float)((double)(0.2f * 128.0f / S3D_DESC_NUMEL));
+    for (int pass = 0; pass < 2; pass++) {
+        double acc = 0.0;
+        for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) {
+            const double v = (double)hist[i];
+            acc = __dadd_rn(acc, __dmul_rn(v, v));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < DESC2_THREADS / 32; i++) tot += s_red[i];
+            s_norm_inv = (float)(1.0 / (sqrt(tot) + DBL_EPSILON));
+        }
+        __syncthreads();
+        const float ninv = s_norm_inv;
+        for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) {
+            float v = fm(hist[i], ninv);
+            if (pass == 0) v = fminf(v, trunc);
+            hist[i] = v;
+        }
+        __syncthreads();
+    }
+    float *o32 = reinterpret_cast<float *>(out + (size_t)ki * S3D_DESC_STRIDE);
+    for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) o32[i] = hist[i];
+    if (tid == 0) {
+        double *o64 = reinterpret_cast<double *>(out + (size_t)ki * S3D_DESC_STRIDE +
+                                                 S3D_DESC_NUMEL * sizeof(float));
+        const double f = ldexp(1.0, kp.o);  // sift.c:1851, 1922-1925
+        o64[0] = (double)kp.x * f;
+        o64[1] = (double)kp.y * f;
+        o64[2] = (double)kp.z * f;
+        o64[3] = kp.sd;
+    }
+}
+
 // ---------------------------------------------------------------- dense descriptors
 // extract_dense_descriptors_no_rotate (sift.c:2462-2480): barycentric weights of
 // the gradient direction, written to three of the twelve channels.
@@ -509,6 +800,9 @@ __global__ void __launch_bounds__(256)
     k_dense_bary(const float *__restrict__ sm, int nx, int ny, int nz, float iux, float iuy,
                  float iuz, const MeshDev *__restrict__ M, float *__restrict__ temp)
 {
+    __shared__ FaceConst s_face[20];
+    load_faces(s_face, M);
+    __syncthreads();
     const size_t total = (size_t)nx * ny * nz;
     const size_t ys = nx, zs = (size_t)nx * ny;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -526,13 +820,13 @@ __global__ void __launch_bounds__(256)
             g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
             g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
             g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
-            const int bin = icos_bin(M, g, bary);
+            const int bin = icos_bin(s_face, g, bary);
             if (bin >= 0) {
 #pragma unroll
                 for (int k = 0; k < 12; k++) {
-                    if (k == M->f[bin].idx[0]) h[k] = bary[0];
-                    if (k == M->f[bin].idx[1]) h[k] = bary[1];
-                    if (k == M->f[bin].idx[2]) h[k] = bary[2];
+                    if (k == s_face[bin].idx[0]) h[k] = bary[0];
+                    if (k == s_face[bin].idx[1]) h[k] = bary[1];
+                    if (k == s_face[bin].idx[2]) h[k] = bary[2];
                 }
             }
         }
@@ -628,6 +922,12 @@ int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx)
     }
     for (int i = 0; i < 12; i++)
         for (int j = 0; j < 3; j++) M.vert[i][j] = 0.0f;
+    {
+        float vm[20][3];
+        for (int i = 0; i < 20; i++)
+            for (int j = 0; j < 3; j++) vm[i][j] = M.f[i].vmid[j];
+        S3D_CUDA(e, cudaMemcpyToSymbol(c_vmid, vm, sizeof(vm)));
+    }
     if (!e->d_mesh) S3D_CUDA(e, cudaMalloc(&e->d_mesh, sizeof(MeshDev)));
     S3D_CUDA(e, cudaMemcpyAsync(e->d_mesh, &M, sizeof(M), cudaMemcpyHostToDevice, e->stream));
     S3D_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -680,7 +980,14 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
     if (n <= 0) return 0;
     if (!e->have_mesh) return s3d_fail(e, "mesh not set", cudaSuccess, __FILE__, __LINE__);
     const PyrTable T = make_table(e);
-    k_descriptor<<<n, DESC_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out, e->opt_icos_fast);
+    // v2 packs window offsets in 10 bits per axis; a window wider than 1023 voxels (absurd
+    // scales) takes the simple kernel
+    if (e->opt_desc_v1)
+        k_descriptor<<<n, DESC_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
+                                                        e->opt_icos_fast);
+    else
+        k_descriptor2<<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
+                                                          e->opt_icos_fast);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

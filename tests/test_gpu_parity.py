@@ -241,8 +241,10 @@ def test_full_size_properties(b200_lib):
         kp2 = s.detect_keypoints(vol * np.float32(4.0))  # im_scale: power-of-2 gain is exact
         d2 = s.extract_descriptors()
     assert len(kp1) > 1000 and s is not None
-    assert np.array_equal(kp1.view(np.uint8), kp2.view(np.uint8))
-    assert rel_l2(d2["hists"], d1["hists"]).max() <= 1e-6  # atomics order only
+    for f in kp1.dtype.names:  # (the raw struct also holds the R pointer: compare fields)
+        assert np.array_equal(kp1[f], kp2[f]), f
+    # fixed-point histogram + static work split: descriptors are bit-reproducible
+    assert np.array_equal(d1["hists"], d2["hists"])
     # (o, s, z, y, x) scan order (sift.c:1154, 1176)
     key = np.stack([kp1["o"], kp1["s"], kp1["zd"], kp1["yd"], kp1["xd"]], 1)
     order = np.lexsort(key.T[::-1])
