@@ -108,12 +108,13 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
     constexpr int D0 = (HWA - HW) & ~1;  // even column where the X window of run 0 starts
     constexpr int SH = (HWA - HW) & 1;   // 1 if the true window starts one column later
     constexpr int LW = 2 * HW + 4 + 2 * SH;  // window length (even)
+    constexpr int NXI = NRP * (TX / 4);  // X-phase items: (row pair, run of 4 outputs)
     static_assert(NRP * AWQ <= NT, "one fill item per thread");
-    static_assert(NRP <= 32, "row pairs map to lanes");
+    static_assert(NXI <= NT, "one X item per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *A = reinterpret_cast<float2 *>(smem_raw);
-    float *B = reinterpret_cast<float *>(A + NRP * APITCH);
-    short *task_plane = reinterpret_cast<short *>(B + NR * BPITCH);  // [<= nz + 2HW + 2]
+    float2 *Abuf = reinterpret_cast<float2 *>(smem_raw);              // 3 x [NRP][APITCH]
+    float *Bbuf = reinterpret_cast<float *>(Abuf + 3 * NRP * APITCH);  // 3 x [NR][BPITCH]
+    short *task_plane = reinterpret_cast<short *>(Bbuf + 3 * NR * BPITCH);
     unsigned char *task_mode = reinterpret_cast<unsigned char *>(task_plane + (P.nz + 2 * HW + 4));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -126,14 +127,16 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
     K.nz = pk(P.c_negzero, P.c_negzero);
     K.one = pk(P.c_one, P.c_one);
     K.pz = pk(P.c_zero, P.c_zero);
-    // lanes 4..7 of every quarter warp swap the order of their two 16-byte stores so that
-    // the eight lanes of a quarter hit eight different bank groups (see fill / X store)
-    const bool swap_st = (lane & 4) != 0;
+
+    // X-phase item of this thread: row pair xrp, run xrun (4 outputs); all 32 lanes of the
+    // first NXI/32 warps are busy
+    const bool x_thread = tid < NXI;
+    const int xrun = tid / NRP, xrp = tid - xrun * NRP;
+    const bool swap_st = (xrp & 4) != 0;  // bank-conflict-free order of the two 16-byte stores
 
     for (int si = P.seg_start[blockIdx.x]; si < P.seg_start[blockIdx.x + 1]; si++) {
         const Seg sg = P.segs[si];
         const int x0 = sg.x0, y0 = sg.y0;
-        const bool ybound = (y0 - HW < 0) || (y0 + TY + HW > ny - 1);
         // ---- task list: samples j = zb-1+HW .. za-HW of the extended z line --------------
         __syncthreads();
         int ntask;
@@ -162,71 +165,124 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
             }
         }
 
-        // ---- per-thread fill item: row pair frp, columns 4*fq..4*fq+3 of the A tile --------
-        const bool fill_thread = tid < NRP * AWQ;
+        // ---- fill item: row pair frp, columns 4*fq..4*fq+3 of the A tile; only groups and rows
+        //      inside the volume are loaded (mirror samples are synthesised by the readers) -----
         const int frp = tid / AWQ, fq = tid - frp * AWQ;
-        const int fy = y0 - HW + 2 * frp;        // global row of the pair's first row
-        const int fx = x0 - HWA + 4 * fq;        // global column of the group's first column
-        const bool cols_in = fx >= 0 && fx + 3 <= nx - 1;  // group inside the volume
-        const bool row0_ok = fill_thread && cols_in && fy >= 0 && fy < ny;
-        const bool row1_ok = fill_thread && cols_in && fy + 1 >= 0 && fy + 1 < ny;
-        // x mirror samples are written by the thread that owns their SOURCE columns, from the
-        // registers it loaded anyway (no extra pass, barrier or exposed latency):
-        //   x < 0      : column -x is a copy of column x            (1 <= x <= HW)
-        //   x >= nx-1  : omf*col[lo] + f*col[lo+1], written by the owner of col lo+1; col lo is
-        //                its previous column (one extra scalar load when lo+1 starts a group)
-        const bool xedge = (x0 - HW < 0) || (x0 + TX + HW > nx - 1);  // block-uniform
-        int lt[4], rk[4];
-        bool need_prev = false;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int x = fx + c;
-            lt[c] = (cols_in && x >= 1 && x <= HW && x0 - HW < 0) ? (-x - (x0 - HWA)) : -1;
-            const int k = nx - 1 - x;  // column x is `hi` of right-mirror sample k
-            const bool r = cols_in && k >= 0 && k <= HW && x >= 1 && nx - 1 + k < x0 + TX + HW;
-            rk[c] = r ? k : -1;
-            if (c == 0 && r) need_prev = true;
-        }
-        const float *g0 = P.src + (size_t)(row0_ok ? fy : 0) * nx;
-        const float *g1 = P.src + (size_t)(row1_ok ? fy + 1 : 0) * nx;
-        float2 *fdst = A + frp * APITCH + 4 * fq;
-
-        // one row of the group: a single aligned 16-byte load (groups outside the volume are
-        // skipped: their columns are mirror samples, synthesised at store time -- see below)
+        const int fy = y0 - HW + 2 * frp;
+        const int fx = x0 - HWA + 4 * fq;
+        const bool fill_thread = tid < NRP * AWQ && fx >= 0 && fx + 3 <= nx - 1;
+        const bool row0_ok = fill_thread && fy >= 0 && fy < ny;
+        const bool row1_ok = fill_thread && fy + 1 >= 0 && fy + 1 < ny;
+        const float *g0 = P.src + (size_t)(row0_ok ? fy : 0) * nx + (fill_thread ? fx : 0);
+        const float *g1 = P.src + (size_t)(row1_ok ? fy + 1 : 0) * nx + (fill_thread ? fx : 0);
+        const int fdst_off = frp * APITCH + 4 * fq;
+        const bool fswap = (lane & 4) != 0;
         auto load4 = [&](const float *row, bool ok) -> float4 {
-            if (!ok) return make_float4(0.f, 0.f, 0.f, 0.f);
-            return __ldg(reinterpret_cast<const float4 *>(row + fx));
+            return ok ? __ldg(reinterpret_cast<const float4 *>(row)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        auto store_item = [&](const float4 a, const float4 b, const float pa, const float pb) {
-            if (!fill_thread || !cols_in) return;  // groups outside the volume hold mirror samples
+        auto store_item = [&](float2 *Adst, const float4 a, const float4 b) {
+            if (!fill_thread) return;
             const float4 lo4 = make_float4(a.x, b.x, a.y, b.y), hi4 = make_float4(a.z, b.z, a.w, b.w);
-            float4 *d = reinterpret_cast<float4 *>(fdst);
-            if (swap_st) {
+            float4 *d = reinterpret_cast<float4 *>(Adst + fdst_off);
+            if (fswap) {
                 d[1] = hi4;
                 d[0] = lo4;
             } else {
                 d[0] = lo4;
                 d[1] = hi4;
             }
-            if (xedge) {
-                float2 *rowp = A + frp * APITCH;
-                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        };
+
+        // ---- X phase: (row pair, 4 outputs) per thread, window streamed right to left ------------
+        auto xphase = [&](const float2 *Asrc, float *Bdst) {
+            if (!x_thread) return;
+            const float2 *arow = Asrc + xrp * APITCH;
+            u64 o0 = K.pz, o1 = K.pz, o2 = K.pz, o3 = K.pz;
+            auto tapstep = [&](int p, u64 v) {  // window position p, descending
+                const int a0 = SH + 2 * HW - p;  // output i uses tap index a0 + i
+                if (a0 >= 0 && a0 < W) o0 = add2(mul2(v, pk(P.taps.t[a0 < 0 || a0 >= W ? 0 : a0], P.taps.t[a0 < 0 || a0 >= W ? 0 : a0]), K), o0, K);
+                if (a0 + 1 >= 0 && a0 + 1 < W) o1 = add2(mul2(v, pk(P.taps.t[a0 + 1 < 0 || a0 + 1 >= W ? 0 : a0 + 1], P.taps.t[a0 + 1 < 0 || a0 + 1 >= W ? 0 : a0 + 1]), K), o1, K);
+                if (a0 + 2 >= 0 && a0 + 2 < W) o2 = add2(mul2(v, pk(P.taps.t[a0 + 2 < 0 || a0 + 2 >= W ? 0 : a0 + 2], P.taps.t[a0 + 2 < 0 || a0 + 2 >= W ? 0 : a0 + 2]), K), o2, K);
+                if (a0 + 3 >= 0 && a0 + 3 < W) o3 = add2(mul2(v, pk(P.taps.t[a0 + 3 < 0 || a0 + 3 >= W ? 0 : a0 + 3], P.taps.t[a0 + 3 < 0 || a0 + 3 >= W ? 0 : a0 + 3]), K), o3, K);
+            };
+            {
+                const float2 *win = arow + 4 * xrun + D0;
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (lt[c] >= 0) rowp[lt[c]] = make_float2(av[c], bv[c]);
-                    if (rk[c] >= 0 && !(P.dbg_flags & 1)) {
-                        const int k = rk[c];
-                        const float om = P.mx.omf[k], ff = P.mx.f[k];
-                        const float p0 = c ? av[c ? c - 1 : 0] : pa, p1 = c ? bv[c ? c - 1 : 0] : pb;
-                        rowp[nx - 1 + k - (x0 - HWA)] =
-                            make_float2(__fadd_rn(__fmul_rn(om, p0), __fmul_rn(ff, av[c])),
-                                        __fadd_rn(__fmul_rn(om, p1), __fmul_rn(ff, bv[c])));
-                    }
+                for (int kk = 0; kk < LW / 2; kk++) {
+                    const ulonglong2 v2 = *reinterpret_cast<const ulonglong2 *>(win + (LW - 2 - 2 * kk));
+                    tapstep(LW - 1 - 2 * kk, v2.y);
+                    tapstep(LW - 2 - 2 * kk, v2.x);
+                }
+            }
+            float a0f, b0f, a1f, b1f, a2f, b2f, a3f, b3f;
+            upk(o0, a0f, b0f);
+            upk(o1, a1f, b1f);
+            upk(o2, a2f, b2f);
+            upk(o3, a3f, b3f);
+            float *brow = Bdst + (2 * xrp) * BPITCH + 4 * xrun;
+            const float4 r0 = make_float4(a0f, a1f, a2f, a3f), r1 = make_float4(b0f, b1f, b2f, b3f);
+            if (swap_st) {
+                *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
+                *reinterpret_cast<float4 *>(brow) = r0;
+            } else {
+                *reinterpret_cast<float4 *>(brow) = r0;
+                *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
+            }
+        };
+
+        // ---- Y phase: rows y = 2*warp, 2*warp+1 of the tile; x pair = lane ---------------------
+        auto yphase = [&](const float *Bsrc, u64 &y0acc, u64 &y1acc) {
+            y0acc = K.pz;
+            y1acc = K.pz;
+            const float *top = Bsrc + 2 * lane + (2 * warp + 1 + 2 * HW) * BPITCH;
+#pragma unroll
+            for (int k = 0; k < W + 1; k++) {  // rows descending from 2*warp+1+HW
+                const u64 v = *reinterpret_cast<const u64 *>(top - k * BPITCH);
+                if (k < W) y1acc = add2(mul2(v, pk(P.taps.t[k < W ? k : 0], P.taps.t[k < W ? k : 0]), K), y1acc, K);
+                if (k >= 1) y0acc = add2(mul2(v, pk(P.taps.t[k >= 1 ? k - 1 : 0], P.taps.t[k >= 1 ? k - 1 : 0]), K), y0acc, K);
+            }
+        };
+
+        // ---- mirror patches (block-uniform; run one step before their consumer, so they need
+        //      no barrier of their own and sit off the critical path) ----------------------------
+        const bool xedge = (x0 - HW < 0) || (x0 + TX + HW > nx - 1);
+        const bool yedge = (y0 - HW < 0) || (y0 + TY + HW > ny - 1);
+        auto xpatch = [&](float2 *Ap) {  // columns of A outside [0, nx-1)
+            const int nl = x0 - HW < 0 ? HW - x0 : 0;
+            const int nrt = x0 + TX + HW > nx - 1 ? x0 + TX + HW - (nx - 1) : 0;
+            const int ncol = nl + nrt;
+            float *Af = reinterpret_cast<float *>(Ap);
+            for (int e = tid; e < NR * ncol; e += NT) {
+                const int r = e / ncol, c = e - r * ncol;
+                const int base = ((r >> 1) * APITCH) * 2 + (r & 1);
+                if (c < nl) {
+                    const int x = x0 - HW + c;  // < 0: copy of column -x
+                    Af[base + 2 * (x - (x0 - HWA))] = Af[base + 2 * (-x - (x0 - HWA))];
+                } else {
+                    const int k = c - nl;  // x = nx-1+k: omf*col[lo] + f*col[lo+1]
+                    const int lo = P.mx.lo[k] - (x0 - HWA);
+                    const float v = __fadd_rn(__fmul_rn(P.mx.omf[k], Af[base + 2 * lo]),
+                                              __fmul_rn(P.mx.f[k], Af[base + 2 * (lo + 1)]));
+                    Af[base + 2 * (nx - 1 + k - (x0 - HWA))] = v;  // k = 0 overwrites its own `hi`
                 }
             }
         };
-        auto load_prev = [&](const float *row, bool ok) -> float {
-            return (need_prev && ok && !(P.dbg_flags & 2)) ? __ldg(row + fx - 1) : 0.f;
+        auto ypatch = [&](float *Bp) {  // rows of B outside [0, ny-1)
+            const int nt_ = y0 - HW < 0 ? HW - y0 : 0;
+            const int nb_ = y0 + TY + HW > ny - 1 ? y0 + TY + HW - (ny - 1) : 0;
+            for (int e = tid; e < (nt_ + nb_) * TX; e += NT) {
+                const int rr = e / TX, x = e - rr * TX;
+                if (rr < nt_) {
+                    const int y = y0 - HW + rr;  // < 0: copy of row -y
+                    Bp[rr * BPITCH + x] = Bp[(rr - 2 * y) * BPITCH + x];
+                } else {
+                    const int k = rr - nt_;  // y = ny-1+k
+                    const int rl = P.my.lo[k] - (y0 - HW);
+                    const float v = __fadd_rn(__fmul_rn(P.my.omf[k], Bp[rl * BPITCH + x]),
+                                              __fmul_rn(P.my.f[k], Bp[(rl + 1) * BPITCH + x]));
+                    Bp[(ny - 1 + k - (y0 - HW)) * BPITCH + x] = v;
+                }
+            }
         };
 
         u64 acc[2][W];  // Z-phase partial sums by age, for the thread's two rows
@@ -234,130 +290,50 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
 #pragma unroll
         for (int a = 0; a < W; a++) acc[0][a] = acc[1][a] = K.pz;
         prevY[0] = prevY[1] = K.pz;
-        __syncthreads();  // task table visible
+        __syncthreads();  // task table visible; previous segment's smem traffic finished
 
-        // Register-staged prefetch.  Narrow filters do too little arithmetic per plane to hide a
-        // DRAM round trip behind one step, so for HW <= 4 (where registers allow) the loads run
-        // TWO planes ahead: (qa, qb) holds plane t+1 and is stored at the end of step t, (na, nb)
-        // receives plane t+2.
-        constexpr bool PF2 = HW <= 4;
-        float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
-        float qpa = 0.f, qpb = 0.f;
-        {   // first plane (and, with PF2, the second)
-            const size_t off = (size_t)task_plane[0] * plane_stride;
-            store_item(load4(g0 + off, row0_ok), load4(g1 + off, row1_ok), load_prev(g0 + off, row0_ok),
-                       load_prev(g1 + off, row1_ok));
-            if (PF2 && ntask > 1) {
-                const size_t off1 = (size_t)task_plane[1] * plane_stride;
-                qa = load4(g0 + off1, row0_ok);
-                qb = load4(g1 + off1, row1_ok);
-                qpa = load_prev(g0 + off1, row0_ok);
-                qpb = load_prev(g1 + off1, row1_ok);
-            }
-        }
-        // output pointer of z = zb + 2HW (moved down one plane per z step)
+        // ---- software pipeline, ONE barrier per step.  In step t (t = -4 .. ntask-1):
+        //        load  plane t+4 -> registers (stored to A[(t+4)%3] at the end of the step)
+        //        patch x mirrors of A(t+3)          (stored at the end of step t-1)
+        //        X     A(t+2) -> B(t+2)             (patched during step t-1)
+        //        patch y mirrors of B(t+1)          (produced during step t-1)
+        //        Y, Z  B(t)                         (patched during step t-1)
+        //      every read is of data completed before this step's barrier; writers and readers of a
+        //      step touch different ring slots, so warps drift freely between barriers.
         float *optr = P.dst + ((size_t)(sg.zb + 2 * HW) * ny + (y0 + 2 * warp)) * nx + x0 + 2 * lane;
         int zout = sg.zb + 2 * HW;
-        dbg_steps += ntask;
-        for (int t = 0; t < ntask; t++) {
-            __syncthreads();  // S1: A holds plane t; B free
-
-            // ---- X phase: warp = run of 4 outputs, lane = row pair --------------------------
-            if (lane < NRP) {
-                const float2 *arow = A + lane * APITCH + 4 * warp + D0;
-                u64 o0 = K.pz, o1 = K.pz, o2 = K.pz, o3 = K.pz;
-#pragma unroll
-                for (int kk = 0; kk < LW / 2; kk++) {
-                    const ulonglong2 v2 = *reinterpret_cast<const ulonglong2 *>(arow + (LW - 2 - 2 * kk));
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int p = LW - 1 - (2 * kk + h);   // window position, descending
-                        const u64 v = h == 0 ? v2.y : v2.x;
-                        // output i sits at window position SH + i + HW: tap index a = SH + i + 2HW - p
-                        const int a0 = SH + 2 * HW - p;
-                        if (a0 >= 0 && a0 < W) o0 = add2(mul2(v, pk(P.taps.t[a0 < 0 || a0 >= W ? 0 : a0], P.taps.t[a0 < 0 || a0 >= W ? 0 : a0]), K), o0, K);
-                        if (a0 + 1 >= 0 && a0 + 1 < W) o1 = add2(mul2(v, pk(P.taps.t[a0 + 1 < 0 || a0 + 1 >= W ? 0 : a0 + 1], P.taps.t[a0 + 1 < 0 || a0 + 1 >= W ? 0 : a0 + 1]), K), o1, K);
-                        if (a0 + 2 >= 0 && a0 + 2 < W) o2 = add2(mul2(v, pk(P.taps.t[a0 + 2 < 0 || a0 + 2 >= W ? 0 : a0 + 2], P.taps.t[a0 + 2 < 0 || a0 + 2 >= W ? 0 : a0 + 2]), K), o2, K);
-                        if (a0 + 3 >= 0 && a0 + 3 < W) o3 = add2(mul2(v, pk(P.taps.t[a0 + 3 < 0 || a0 + 3 >= W ? 0 : a0 + 3], P.taps.t[a0 + 3 < 0 || a0 + 3 >= W ? 0 : a0 + 3]), K), o3, K);
-                    }
-                }
-                float a0f, b0f, a1f, b1f, a2f, b2f, a3f, b3f;
-                upk(o0, a0f, b0f);
-                upk(o1, a1f, b1f);
-                upk(o2, a2f, b2f);
-                upk(o3, a3f, b3f);
-                float *brow = B + (2 * lane) * BPITCH + 4 * warp;
-                const float4 r0 = make_float4(a0f, a1f, a2f, a3f), r1 = make_float4(b0f, b1f, b2f, b3f);
-                if (swap_st) {
-                    *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
-                    *reinterpret_cast<float4 *>(brow) = r0;
-                } else {
-                    *reinterpret_cast<float4 *>(brow) = r0;
-                    *reinterpret_cast<float4 *>(brow + BPITCH) = r1;
-                }
-                if (ybound && !(P.dbg_flags & 4)) {
-                    // rows outside [0, ny-1) are synthesised here, from registers, by the thread
-                    // that owns their source rows (no extra pass, no extra barrier):
-                    //   y < 0      : copy of row -y
-                    //   y >= ny-1  : omf*row[lo] + f*row[lo+1]; the thread owning row lo+1 writes
-                    //                it, taking row lo from its own pair or from the lane below
-                    const int ya = y0 - HW + 2 * lane;  // global y of the pair's first row
-                    constexpr unsigned xmask = NRP >= 32 ? 0xffffffffu : ((1u << NRP) - 1u);
-                    const float4 below = make_float4(__shfl_up_sync(xmask, r1.x, 1),
-                                                     __shfl_up_sync(xmask, r1.y, 1),
-                                                     __shfl_up_sync(xmask, r1.z, 1),
-                                                     __shfl_up_sync(xmask, r1.w, 1));
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int y = ya + h;
-                        const float4 cur = h ? r1 : r0;
-                        const float4 prv = h ? r0 : below;  // row y-1
-                        if (y >= 1 && y <= HW && -y >= y0 - HW)  // top mirror target row -y
-                            *reinterpret_cast<float4 *>(B + (-y - (y0 - HW)) * BPITCH + 4 * warp) = cur;
-                        const int k = ny - 1 - y;  // this row is `hi` of mirror sample k
-                        if (k >= 0 && k <= HW && y >= 1 && ny - 1 + k < y0 + TY + HW) {
-                            const float om = P.my.omf[k], ff = P.my.f[k];
-                            float4 v;
-                            v.x = __fadd_rn(__fmul_rn(om, prv.x), __fmul_rn(ff, cur.x));
-                            v.y = __fadd_rn(__fmul_rn(om, prv.y), __fmul_rn(ff, cur.y));
-                            v.z = __fadd_rn(__fmul_rn(om, prv.z), __fmul_rn(ff, cur.z));
-                            v.w = __fadd_rn(__fmul_rn(om, prv.w), __fmul_rn(ff, cur.w));
-                            // k = 0 overwrites row ny-1 itself: done after the plain store above
-                            *reinterpret_cast<float4 *>(B + (ny - 1 + k - (y0 - HW)) * BPITCH + 4 * warp) = v;
-                        }
-                    }
-                }
-            }
-            __syncthreads();  // S2: B complete, A free
-
-            // prefetch into registers; stored to A after the Z phase
+        dbg_steps += ntask + 4;
+        // narrow filters do too little work per step to hide a DRAM round trip inside ONE step:
+        // with PF2 the loads are issued a step earlier and parked in a second register set
+        constexpr bool PF2 = HW <= 3;  // measured: helps w=5,7; hurts w>=9 (register pressure)
+        float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+        for (int t = PF2 ? -5 : -4; t < ntask; t++) {
+            __syncthreads();
             float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-            float npa = 0.f, npb = 0.f;
-            const bool more = t + 1 < ntask;
+            const bool ld = t + 4 < ntask;  // plane t+4 is stored at the end of this step
             {
-                const int tp = PF2 ? t + 2 : t + 1;
-                if (tp < ntask) {
-                    const size_t off = (size_t)task_plane[tp] * plane_stride;
+                const int tl = PF2 ? t + 5 : t + 4;
+                if (tl >= 0 && tl < ntask) {
+                    const size_t off = (size_t)task_plane[tl] * plane_stride;
                     na = load4(g0 + off, row0_ok);
                     nb = load4(g1 + off, row1_ok);
-                    if (xedge) {
-                        npa = load_prev(g0 + off, row0_ok);
-                        npb = load_prev(g1 + off, row1_ok);
-                    }
                 }
             }
-
-            // ---- Y phase: rows y = 2*warp, 2*warp+1; x pair = lane ---------------------------
-            u64 y0acc = K.pz, y1acc = K.pz;
-            {
-                const float *bcol = B + (2 * warp + 1 + 2 * HW) * BPITCH + 2 * lane;
-#pragma unroll
-                for (int k = 0; k < W + 1; k++) {  // rows descending from 2*warp+1+HW
-                    const u64 v = *reinterpret_cast<const u64 *>(bcol - k * BPITCH);
-                    if (k < W) y1acc = add2(mul2(v, pk(P.taps.t[k < W ? k : 0], P.taps.t[k < W ? k : 0]), K), y1acc, K);
-                    if (k >= 1) y0acc = add2(mul2(v, pk(P.taps.t[k >= 1 ? k - 1 : 0], P.taps.t[k >= 1 ? k - 1 : 0]), K), y0acc, K);
+            if (xedge && t + 3 >= 0 && t + 3 < ntask) xpatch(Abuf + ((t + 3) % 3) * NRP * APITCH);
+            if (t + 2 >= 0 && t + 2 < ntask)
+                xphase(Abuf + ((t + 2) % 3) * NRP * APITCH, Bbuf + ((t + 2) % 3) * NR * BPITCH);
+            if (yedge && t + 1 >= 0 && t + 1 < ntask) ypatch(Bbuf + ((t + 1) % 3) * NR * BPITCH);
+            if (t < 0) {
+                if (PF2) {
+                    if (ld && t + 4 >= 0) store_item(Abuf + ((t + 4) % 3) * NRP * APITCH, qa, qb);
+                    qa = na, qb = nb;
+                } else if (ld) {
+                    store_item(Abuf + ((t + 4) % 3) * NRP * APITCH, na, nb);
                 }
+                continue;
             }
+            u64 y0acc, y1acc;
+            yphase(Bbuf + (t % 3) * NR * BPITCH, y0acc, y1acc);
 
             // ---- Z phase --------------------------------------------------------------------
             const int mode = task_mode[t];
@@ -395,11 +371,11 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
                 }
             }
             if (PF2) {
-                if (more) store_item(qa, qb, qpa, qpb);
-                qa = na, qb = nb, qpa = npa, qpb = npb;
-            } else if (more) {
-                store_item(na, nb, npa, npb);
-            }  // A is free since S2; visible after the next S1
+                if (ld) store_item(Abuf + ((t + 4) % 3) * NRP * APITCH, qa, qb);
+                qa = na, qb = nb;
+            } else if (ld) {
+                store_item(Abuf + ((t + 4) % 3) * NRP * APITCH, na, nb);
+            }
         }
     }
     if (P.dbg && tid == 0) {
@@ -415,7 +391,7 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
 size_t smem_bytes(int hw, int nz)
 {
     const int NR = TY + 2 * hw;
-    size_t b = (size_t)(NR / 2) * APITCH * sizeof(float2) + (size_t)NR * BPITCH * sizeof(float);
+    size_t b = (size_t)3 * (NR / 2) * APITCH * sizeof(float2) + (size_t)3 * NR * BPITCH * sizeof(float);
     b += (size_t)(nz + 2 * hw + 4) * sizeof(short) + (size_t)(nz + 2 * hw + 4);
     return (b + 15) & ~(size_t)15;
 }
@@ -492,10 +468,10 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
         for (long c = 0; c < ncol; c++) {
             const int x0 = xs[c % xs.size()], y0 = ys[c / xs.size()];
             double w = 1.0;
-            if (x0 - hw < 0) w *= 1.11;
-            if (x0 + TX + hw > nx - 1) w *= 1.30;
-            if (y0 - hw < 0) w *= 1.06;
-            if (y0 + TY + hw > ny - 1) w *= 1.19;
+            if (x0 - hw < 0) w *= e->blur_w[0];
+            if (x0 + TX + hw > nx - 1) w *= e->blur_w[1];
+            if (y0 - hw < 0) w *= e->blur_w[2];
+            if (y0 + TY + hw > ny - 1) w *= e->blur_w[3];
             wcol[c] = w;
             wsum += w * nz;
         }
