@@ -272,33 +272,36 @@ class Sift3D:
         self.L.init_SIFT3D_Descriptor_store(C.byref(self.desc))
 
     # -- the three hot API calls ------------------------------------------------
-    def detect_keypoints(self, vol: np.ndarray, units=(1.0, 1.0, 1.0)) -> np.ndarray:
-        """`SIFT3D_detect_keypoints` (sift.c:1609).  Returns a KEYPOINT_DTYPE array (copy)."""
+    def detect_keypoints(self, vol: np.ndarray, units=(1.0, 1.0, 1.0), copy: bool = True):
+        """`SIFT3D_detect_keypoints` (sift.c:1609).  Returns a KEYPOINT_DTYPE array."""
         im = make_image(np.ascontiguousarray(vol, np.float32), units)
         rc = self.L.SIFT3D_detect_keypoints(C.byref(self.s), C.byref(im), C.byref(self.kp))
         if rc != 0:
             raise RuntimeError(f"SIFT3D_detect_keypoints returned {rc}")
-        return self.keypoints()
+        return self.keypoints(copy)
 
-    def keypoints(self) -> np.ndarray:
+    def keypoints(self, copy: bool = True) -> np.ndarray:
+        """Keypoint records; copy=False returns a view of the store (valid until the next call)."""
         n = self.kp.slab.num
         if n == 0:
             return np.zeros(0, KEYPOINT_DTYPE)
         buf = (C.c_char * (n * 112)).from_address(C.addressof(self.kp.buf.contents))
-        return np.frombuffer(buf, dtype=KEYPOINT_DTYPE, count=n).copy()
+        a = np.frombuffer(buf, dtype=KEYPOINT_DTYPE, count=n)
+        return a.copy() if copy else a
 
-    def extract_descriptors(self) -> np.ndarray:
+    def extract_descriptors(self, copy: bool = True) -> np.ndarray:
         """`SIFT3D_extract_descriptors` (sift.c:2025) on the stored keypoints."""
         rc = self.L.SIFT3D_extract_descriptors(C.byref(self.s), C.byref(self.kp),
                                                C.byref(self.desc))
         if rc != 0:
             raise RuntimeError(f"SIFT3D_extract_descriptors returned {rc}")
-        return self.descriptors()
+        return self.descriptors(copy)
 
-    def descriptors(self) -> np.ndarray:
+    def descriptors(self, copy: bool = True) -> np.ndarray:
         n = self.desc.num
         buf = (C.c_char * (n * 3104)).from_address(C.addressof(self.desc.buf.contents))
-        return np.frombuffer(buf, dtype=DESCRIPTOR_DTYPE, count=n).copy()
+        a = np.frombuffer(buf, dtype=DESCRIPTOR_DTYPE, count=n)
+        return a.copy() if copy else a
 
     def extract_dense_descriptors(self, vol: np.ndarray, units=(1.0, 1.0, 1.0)) -> np.ndarray:
         """`SIFT3D_extract_dense_descriptors` (sift.c:2354).  Returns [z][y][x][12] float32."""

@@ -58,6 +58,7 @@ struct s3d_engine {
     int num_sms = S3D_NUM_SMS_FALLBACK;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of descriptor chunks behind the kernel
     std::string err;
     long long launches = 0;
     int blur_mode = 0;

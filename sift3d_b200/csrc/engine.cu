@@ -171,6 +171,7 @@ void s3d_engine_destroy(s3d_engine *e)
     for (auto &t : e->segtabs)
         if (t.d) cudaFree(t.d);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
 }
 
@@ -510,9 +511,32 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
         e->desc_cap = bytes;
     }
     S3D_CUDA(e, cudaMemcpyAsync(e->d_kp_in, kp, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyHostToDevice, e->stream));
-    if (s3d_k_descriptors(e, e->d_kp_in, n, e->d_desc)) return -1;
-    S3D_CUDA(e, cudaMemcpyAsync(host_desc, e->d_desc, bytes, cudaMemcpyDeviceToHost, e->stream));
-    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    // chunked: the D2H copy of chunk i (on a second stream) overlaps the kernel of chunk i+1, so
+    // the 3104 B/keypoint of results leave the device behind the compute instead of after it
+    if (!e->copy_stream) S3D_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    const int chunk = 4096;
+    const int nchunks = (n + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> done(nchunks);
+    int rc = 0;
+    for (int c = 0; c < nchunks && !rc; c++) {
+        const int lo = c * chunk, cnt = std::min(chunk, n - lo);
+        rc = s3d_k_descriptors(e, e->d_kp_in + lo, cnt, e->d_desc + (size_t)lo * S3D_DESC_STRIDE);
+        if (rc) break;
+        if (cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(done[c], e->stream) != cudaSuccess ||
+            cudaStreamWaitEvent(e->copy_stream, done[c], 0) != cudaSuccess ||
+            cudaMemcpyAsync((unsigned char *)host_desc + (size_t)lo * S3D_DESC_STRIDE,
+                            e->d_desc + (size_t)lo * S3D_DESC_STRIDE, (size_t)cnt * S3D_DESC_STRIDE,
+                            cudaMemcpyDeviceToHost, e->copy_stream) != cudaSuccess)
+            rc = s3d_fail(e, "descriptor download", cudaGetLastError(), __FILE__, __LINE__);
+    }
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    cudaError_t ce2 = cudaStreamSynchronize(e->copy_stream);
+    for (int c = 0; c < nchunks; c++)
+        if (done[c]) cudaEventDestroy(done[c]);
+    if (rc) return -1;
+    if (ce != cudaSuccess || ce2 != cudaSuccess)
+        return s3d_fail(e, "descriptor download", ce != cudaSuccess ? ce : ce2, __FILE__, __LINE__);
     return 0;
 }
 

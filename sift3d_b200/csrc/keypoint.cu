@@ -30,6 +30,9 @@ __device__ __forceinline__ float dot3(float a, float b, float c, float d, float 
 
 // unit centroid directions of the 20 faces: uniform (unrolled) access -> constant bank operands
 __constant__ float c_vmid[20][3];
+// face index by (dodecahedron vertex family, sign bits of g): the 20 face centroids are the
+// vertices (+-1,+-1,+-1), (+-1/phi,0,+-phi), (+-phi,+-1/phi,0), (0,+-phi,+-1/phi) of a dodecahedron
+__constant__ int c_face_lut[32];
 
 // cart2bary (sift.c:335-394) with the per-face constants hoisted.
 __device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], float bary[3])
@@ -54,23 +57,27 @@ __device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], 
 // is the containing face; if its barycentrics are all comfortably positive no
 // other face can pass (faces only overlap within bary_eps of shared edges), so
 // it is also the first.  Otherwise fall back to the literal in-order loop.
-__device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, const float g[3],
-                                        float bary[3], const bool fast = true)
+__device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, const int *lut,
+                                        const float g[3], float bary[3], const bool fast = true)
 {
     const float n2 = fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2]));
     if ((double)n2 < K_BARY_EPS) return -1;
     if (fast) {
-        // preselect by centroid direction (any proxy is fine: the choice is verified)
-        int best = 0;
-        float bd = -FLT_MAX;
-#pragma unroll
-        for (int i = 0; i < 20; i++) {
-            const float d = g[0] * c_vmid[i][0] + g[1] * c_vmid[i][1] + g[2] * c_vmid[i][2];
-            if (d > bd) {
-                bd = d;
-                best = i;
-            }
-        }
+        // Preselect the face whose centroid is closest to g.  By symmetry only four of the twenty
+        // centroid dot products can be the largest -- one per vertex family of the dual
+        // dodecahedron, with the signs of g -- so 4 candidates replace 20 (the choice is then
+        // VERIFIED with the exact test, so a wrong guess only costs the fallback loop).
+        const float ax = fabsf(g[0]), ay = fabsf(g[1]), az = fabsf(g[2]);
+        const float PHI = 1.6180339887f, IPH = 0.6180339887f;
+        const float s0 = ax + ay + az, s1 = ax * IPH + az * PHI, s2 = ax * PHI + ay * IPH,
+                    s3 = ay * PHI + az * IPH;
+        int type = 0;
+        float bs = s0;
+        if (s1 > bs) bs = s1, type = 1;
+        if (s2 > bs) bs = s2, type = 2;
+        if (s3 > bs) bs = s3, type = 3;
+        const int sb = (g[0] < 0.0f ? 1 : 0) | (g[1] < 0.0f ? 2 : 0) | (g[2] < 0.0f ? 4 : 0);
+        const int best = lut[type * 8 + sb];
         const float margin = 1e-4f;
         if (face_test(F[best], g, bary) && bary[0] > margin && bary[1] > margin &&
             bary[2] > margin)
@@ -82,8 +89,10 @@ __device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, 
 }
 
 // stage the per-face constants in shared memory (divergent indexing by face)
-__device__ __forceinline__ void load_faces(FaceConst *s_face, const MeshDev *__restrict__ M)
+__device__ __forceinline__ void load_faces(FaceConst *s_face, int *s_lut,
+                                           const MeshDev *__restrict__ M)
 {
+    if (threadIdx.x < 32) s_lut[threadIdx.x] = c_face_lut[threadIdx.x];
     const int nw = 20 * (int)(sizeof(FaceConst) / 4);
     const unsigned *src = reinterpret_cast<const unsigned *>(M->f);
     unsigned *dst = reinterpret_cast<unsigned *>(s_face);
@@ -416,10 +425,11 @@ __global__ void __launch_bounds__(DESC_THREADS)
     __shared__ float s_norm_inv;
     __shared__ unsigned long long s_tab[32];
     __shared__ FaceConst s_face[20];
+    __shared__ int s_lut[32];
     const int ki = blockIdx.x;
     if (ki >= n) return;
     if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
-    load_faces(s_face, M);
+    load_faces(s_face, s_lut, M);
     const s3d_keypoint kp = kps[ki];
     const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
     const float *__restrict__ im = T.ptrs[lv];
@@ -486,7 +496,7 @@ __global__ void __launch_bounds__(DESC_THREADS)
         for (int a = 0; a < 3; a++)
             gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
         float bary[3];
-        const int bin = icos_bin(s_face, gr, bary, icos_fast != 0);
+        const int bin = icos_bin(s_face, s_lut, gr, bary, icos_fast != 0);
         if (bin < 0) continue;
         const float mag = __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
         float dv[3];
@@ -570,7 +580,7 @@ __global__ void __launch_bounds__(DESC_THREADS)
 #define DESC2_THREADS 256
 #define DESC2_LIST 9216  // entries; split into one segment per warp
 
-__global__ void __launch_bounds__(DESC2_THREADS)
+__global__ void __launch_bounds__(DESC2_THREADS, 4)
     k_descriptor2(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
@@ -581,6 +591,7 @@ __global__ void __launch_bounds__(DESC2_THREADS)
     __shared__ unsigned long long s_tab[32];
     __shared__ double s_red[DESC2_THREADS / 32];
     __shared__ FaceConst s_face[20];
+    __shared__ int s_lut[32];
     __shared__ float s_norm_inv;
     __shared__ int s_segcount[DESC2_THREADS / 32];
     const int ki = blockIdx.x;
@@ -615,7 +626,7 @@ __global__ void __launch_bounds__(DESC2_THREADS)
         h_hi[i] = 0;
     }
     if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
-    load_faces(s_face, M);
+    load_faces(s_face, s_lut, M);
     __syncthreads();
 
     const int bx = max(x1 - x0 + 1, 0), by = max(y1 - y0 + 1, 0), bz = max(z1 - z0 + 1, 0);
@@ -710,7 +721,7 @@ __global__ void __launch_bounds__(DESC2_THREADS)
             for (int a = 0; a < 3; a++)
                 gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
             float bary[3];
-            const int bin = icos_bin(s_face, gr, bary, icos_fast != 0);
+            const int bin = icos_bin(s_face, s_lut, gr, bary, icos_fast != 0);
             if (bin < 0) continue;
             const float mag =
                 __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
@@ -801,7 +812,8 @@ __global__ void __launch_bounds__(256)
                  float iuz, const MeshDev *__restrict__ M, float *__restrict__ temp)
 {
     __shared__ FaceConst s_face[20];
-    load_faces(s_face, M);
+    __shared__ int s_lut[32];
+    load_faces(s_face, s_lut, M);
     __syncthreads();
     const size_t total = (size_t)nx * ny * nz;
     const size_t ys = nx, zs = (size_t)nx * ny;
@@ -820,7 +832,7 @@ __global__ void __launch_bounds__(256)
             g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
             g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
             g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
-            const int bin = icos_bin(s_face, g, bary);
+            const int bin = icos_bin(s_face, s_lut, g, bary);
             if (bin >= 0) {
 #pragma unroll
                 for (int k = 0; k < 12; k++) {
@@ -927,6 +939,22 @@ int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx)
         for (int i = 0; i < 20; i++)
             for (int j = 0; j < 3; j++) vm[i][j] = M.f[i].vmid[j];
         S3D_CUDA(e, cudaMemcpyToSymbol(c_vmid, vm, sizeof(vm)));
+        const double ph = 1.6180339887, ip = 1.0 / ph;
+        const double rep[4][3] = {{1, 1, 1}, {ip, 0, ph}, {ph, ip, 0}, {0, ph, ip}};
+        int lut[32];
+        for (int t = 0; t < 4; t++)
+            for (int sb = 0; sb < 8; sb++) {
+                const double v[3] = {(sb & 1 ? -1 : 1) * rep[t][0], (sb & 2 ? -1 : 1) * rep[t][1],
+                                     (sb & 4 ? -1 : 1) * rep[t][2]};
+                int bi = 0;
+                double bd = -1e30;
+                for (int i = 0; i < 20; i++) {
+                    const double d = v[0] * vm[i][0] + v[1] * vm[i][1] + v[2] * vm[i][2];
+                    if (d > bd) bd = d, bi = i;
+                }
+                lut[t * 8 + sb] = bi;
+            }
+        S3D_CUDA(e, cudaMemcpyToSymbol(c_face_lut, lut, sizeof(lut)));
     }
     if (!e->d_mesh) S3D_CUDA(e, cudaMalloc(&e->d_mesh, sizeof(MeshDev)));
     S3D_CUDA(e, cudaMemcpyAsync(e->d_mesh, &M, sizeof(M), cudaMemcpyHostToDevice, e->stream));
