@@ -585,15 +585,14 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
     __shared__ unsigned list[DESC2_LIST];
-    __shared__ unsigned h_lo[S3D_DESC_NUMEL + 1];  // +1: dummy slot for out-of-grid corners
-    __shared__ int h_hi[S3D_DESC_NUMEL + 1];
+    __shared__ unsigned h_lo[S3D_DESC_NUMEL + 32];  // +32: per-lane dummy slots (out-of-grid corners)
+    __shared__ int h_hi[S3D_DESC_NUMEL + 32];
     float *hist = reinterpret_cast<float *>(list);  // the list is dead when hist is written
     __shared__ unsigned long long s_tab[32];
     __shared__ double s_red[DESC2_THREADS / 32];
     __shared__ FaceConst s_face[20];
     __shared__ int s_lut[32];
     __shared__ float s_norm_inv;
-    __shared__ int s_segcount[DESC2_THREADS / 32];
     const int ki = blockIdx.x;
     if (ki >= n) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -621,7 +620,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
 #pragma unroll
         for (int j = 0; j < 3; j++) Rt[3 * i + j] = kp.R[3 * j + i];
 
-    for (int i = tid; i < S3D_DESC_NUMEL + 1; i += DESC2_THREADS) {
+    for (int i = tid; i < S3D_DESC_NUMEL + 32; i += DESC2_THREADS) {
         h_lo[i] = 0u;
         h_hi[i] = 0;
     }
@@ -652,20 +651,23 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
         return inside;
     };
 
-    // rows of a batch are split statically among the warps and every warp appends to its own
-    // list segment, so the list is the same on every run
+    // Every warp works alone until the final reduction: it owns the rows w, w+8, w+16, ... of
+    // the window box (interleaved for balance), compacts the voxels that pass the exact sphere /
+    // cube tests of a chunk of those rows into ITS list segment (phase A, ballot prefix, no
+    // atomics) and immediately consumes the segment (phase B).  Only __syncwarp between the two;
+    // the static split makes the whole computation -- list order included -- deterministic.
     constexpr int NWARP = DESC2_THREADS / 32;
     constexpr int SEGCAP = DESC2_LIST / NWARP;
-    const int rows_per_warp = max(SEGCAP / bx_safe, 1);
-    const int rows_per_batch2 = rows_per_warp * NWARP;
+    const int rows_per_chunk = max(SEGCAP / bx_safe, 1);
     (void)rows_per_batch;
-    for (int rb = 0; rb < nrows && bx > 0; rb += rows_per_batch2) {
-        // ---------------- phase A: scan + compact ------------------------------------------
-        int mycount = 0;  // entries in this warp's segment (warp-uniform)
-        unsigned *seg = list + warp * SEGCAP;
-        for (int i = 0; i < rows_per_warp; i++) {
-            const int row = rb + warp * rows_per_warp + i;
-            if (row >= nrows) break;
+    unsigned *seg = list + warp * SEGCAP;
+    const int my_rows = bx > 0 && nrows > warp ? (nrows - warp + NWARP - 1) / NWARP : 0;
+    for (int rc = 0; rc < my_rows; rc += rows_per_chunk) {
+        // ---------------- phase A: scan + compact (warp-local) -------------------------------
+        int count = 0;  // warp-uniform
+        const int rce = min(rc + rows_per_chunk, my_rows);
+        for (int i = rc; i < rce; i++) {
+            const int row = warp + NWARP * i;
             const int y = y0 + row % by, z = z0 + row / by;
             const float dy = fm(fs((float)y, kp.y), uyf), dz = fm(fs((float)z, kp.z), uzf);
             const float rem = r2 - (dy * dy + dz * dz);
@@ -678,30 +680,21 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                 const bool ok = x <= xb && geom(x, y, z, sq, vb);
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (ok)
-                    seg[mycount + __popc(m & ((1u << lane) - 1u))] =
+                    seg[count + __popc(m & ((1u << lane) - 1u))] =
                         (unsigned)(x - x0) | ((unsigned)(y - y0) << 10) | ((unsigned)(z - z0) << 20);
-                mycount += __popc(m);
+                count += __popc(m);
             }
         }
-        if (lane == 0) s_segcount[warp] = mycount;
-        __syncthreads();
-        int pre[NWARP + 1];
-        pre[0] = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; w++) pre[w + 1] = pre[w] + s_segcount[w];
-        const int count = pre[NWARP];
+        __syncwarp();
         // ---------------- phase B: per-voxel work ---------------------------------------------
-        // thread t owns the contiguous virtual range [t*L, t*L+L): consecutive voxels of a
-        // thread are x-neighbours (long list locality), the lanes of a warp are L apart
-        const int L = (count + DESC2_THREADS - 1) / DESC2_THREADS;
-        const int tperm = lane * NWARP + warp;  // neighbouring lanes far apart in the list
+        // lane l owns the contiguous entries [l*L, l*L+L): its consecutive voxels are x
+        // neighbours (cache-friendly loads) while the 32 lanes sit L entries apart, i.e. in
+        // different spatial cells most of the time (few same-address atomics)
+        const int L = (count + 31) >> 5;
         for (int k = 0; k < L; k++) {
-            const int e = tperm * L + k;
+            const int e = lane * L + k;
             if (e >= count) break;
-            int w = 0;
-#pragma unroll
-            for (int q = 1; q < NWARP; q++) w += (e >= pre[q]) ? 1 : 0;
-            const unsigned code = list[w * SEGCAP + (e - pre[w])];
+            const unsigned code = seg[e];
             const int x = x0 + (int)(code & 1023u), y = y0 + (int)((code >> 10) & 1023u),
                       z = z0 + (int)(code >> 20);
             float sq, vb[3];
@@ -736,7 +729,9 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const int cx = ib[0] + (c >> 2), cy = ib[1] + ((c >> 1) & 1), cz = ib[2] + (c & 1);
-                const bool in = cx < 4 && cy < 4 && cz < 4;  // corners outside the grid add nothing
+                // corners outside the 4x4x4 grid add nothing: they are steered to a per-lane
+                // dummy slot so that the scatter stays branch-free
+                const bool in = cx < 4 && cy < 4 && cz < 4;
                 const int cell = 12 * (cx + 4 * cy + 16 * cz);
                 const float wgt = fm(fm((c >> 2) ? dv[0] : fs(1.0f, dv[0]),
                                         ((c >> 1) & 1) ? dv[1] : fs(1.0f, dv[1])),
@@ -744,19 +739,18 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                 const float mw = fm(mag, wgt);  // (mag * weight) * bary_j, sift.c:1763-1765
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    const int b = cell + (j == 0 ? i0 : (j == 1 ? i1 : i2));
+                    const int b = in ? cell + (j == 0 ? i0 : (j == 1 ? i1 : i2)) : S3D_DESC_NUMEL + lane;
                     const long long q = __float2ll_rn(fm(fm(mw, bary[j]), 4294967296.0f));
                     const unsigned ql = (unsigned)q;
-                    if (in) {
-                        const unsigned old = atomicAdd(&h_lo[b], ql);
-                        const int qh = (int)(q >> 32) + ((old + ql) < old ? 1 : 0);
-                        if (qh) atomicAdd(&h_hi[b], qh);
-                    }
+                    const unsigned old = atomicAdd(&h_lo[b], ql);
+                    const int qh = (int)(q >> 32) + ((old + ql) < old ? 1 : 0);
+                    if (qh) atomicAdd(&h_hi[b], qh);  // carry / sign word: rare
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
+    __syncthreads();
 
     // fixed point -> f32
     for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) {
