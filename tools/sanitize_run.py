@@ -1,0 +1,18 @@
+"""Small run touching every kernel (compute-sanitizer target)."""
+import ctypes as C, sys
+from pathlib import Path
+import numpy as np
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from sift3d_b200 import capi
+from sift3d_b200.volumes import blob_volume
+vol = blob_volume((40, 48, 72), seed=2)   # fused blur eligible (nx>=64, ny>=32), odd tile overlap
+lib = capi.load_b200()
+with capi.Sift3D(lib) as s:
+    kp = s.detect_keypoints(vol)
+    d = s.extract_descriptors()
+    dd = s.extract_dense_descriptors(np.ascontiguousarray(vol[:20, :24, :32]))
+    im = capi.make_image(vol)
+    assert lib.lib.SIFT3D_extract_raw_descriptors(C.byref(s.s), C.byref(im), C.byref(s.kp), C.byref(s.desc)) == 0
+    conf = C.POINTER(C.c_double)()
+    assert lib.lib.SIFT3D_assign_orientations(C.byref(s.s), C.byref(im), C.byref(s.kp), C.byref(conf)) == 0
+print("ok", len(kp), d.shape, dd.shape)
