@@ -125,6 +125,15 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
                           const double desc_units[3], const s3d_filter *smooth,
                           const s3d_filter *window, float *host_out);
 
+/* SIFT3D_extract_dense_descriptors, dense_rotate = 1 (sift.c:2521-2588, :2295-2343):
+ * per voxel, assign_orientation_thresh with sigma = ori_sigma (identity when rejected),
+ * then one 12-bin histogram over a sphere of radius 2 * desc_sigma, gradients rotated by
+ * R^T; post-processing as in the no-rotate path.  host_out: nx*ny*nz*12 floats. */
+int s3d_dense_descriptors_rotate(s3d_engine *e, const float *host_in, int nx, int ny, int nz,
+                                 size_t xs, size_t ys, size_t zs, const double units[3],
+                                 const s3d_filter *smooth, double ori_sigma, double desc_sigma,
+                                 double corner_thresh, float *host_out);
+
 /* Host copy of a pyramid level (which: 0 = Gaussian, 1 = DoG). */
 int s3d_level_download(s3d_engine *e, int which, int o, int s, float *host_dst);
 int s3d_pyramid_copy(s3d_engine *dst, const s3d_engine *src); /* copy_Pyramid, imutil.c:3995 */

@@ -769,9 +769,65 @@ static void normalize12(float *h)
     for (i = 0; i < 12; i++) h[i] *= norm_inv;
 }
 
+/* extract_dense_descrip_rotate (sift.c:2295-2343): one 12-bin histogram over a sphere of
+ * radius desc_rad_fctr * sigma, gradients rotated by R^T, Gaussian window weight. */
+static void dense_descrip_rotate(const OrcCtx *c, const Level *im, const float vc[3],
+                                 double sigma, const float R[9], float hist[12])
+{
+    const float win_radius = k_desc_rad_fctr * sigma;
+    const float uxf = (float)im->u[0], uyf = (float)im->u[1], uzf = (float)im->u[2];
+    const int x_start = ORC_MAX(floorf(vc[0] - win_radius / uxf), 1);
+    const int x_end = ORC_MIN(ceilf(vc[0] + win_radius / uxf), im->n[0] - 2);
+    const int y_start = ORC_MAX(floorf(vc[1] - win_radius / uyf), 1);
+    const int y_end = ORC_MIN(ceilf(vc[1] + win_radius / uyf), im->n[1] - 2);
+    const int z_start = ORC_MAX(floorf(vc[2] - win_radius / uzf), 1);
+    const int z_end = ORC_MIN(ceilf(vc[2] + win_radius / uzf), im->n[2] - 2);
+    const long ys = im->n[0], zs = (long)im->n[0] * im->n[1];
+    float Rt[9];
+    int i, j, x, y, z;
+
+    for (i = 0; i < 3; i++)
+        for (j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+    for (i = 0; i < 12; i++) hist[i] = 0.0f;
+    for (z = z_start; z <= z_end; z++)
+        for (y = y_start; y <= y_end; y++)
+            for (x = x_start; x <= x_end; x++) {
+                const float dx = ((float)x - vc[0]) * uxf;
+                const float dy = ((float)y - vc[1]) * uyf;
+                const float dz = ((float)z - vc[2]) * uzf;
+                const float sq_dist = dx * dx + dy * dy + dz * dz;
+                const float *p = im->d + x + y * ys + z * zs;
+                float grad[3], grot[3], bary[3], mag, weight;
+                int bin;
+                if (sq_dist > win_radius * win_radius) continue;
+                grad[0] = 0.5f * (p[1] - p[-1]);
+                grad[1] = 0.5f * (p[ys] - p[-ys]);
+                grad[2] = 0.5f * (p[zs] - p[-zs]);
+                grad[0] *= 1.0f / uxf;
+                grad[1] *= 1.0f / uyf;
+                grad[2] *= 1.0f / uzf;
+                for (i = 0; i < 3; i++)
+                    grot[i] =
+                        Rt[3 * i] * grad[0] + Rt[3 * i + 1] * grad[1] + Rt[3 * i + 2] * grad[2];
+                if (icos_hist_bin(c, grot, bary, &bin)) continue;
+                /* magnitude of the UNROTATED gradient (sift.c:2330) */
+                mag = sqrtf(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);
+                weight = expf(-0.5f * sq_dist / (sigma * sigma)); /* sift.c:2333, f64 divide */
+                hist[c->tri_idx[bin][0]] += mag * weight * bary[0];
+                hist[c->tri_idx[bin][1]] += mag * weight * bary[1];
+                hist[c->tri_idx[bin][2]] += mag * weight * bary[2];
+            }
+}
+
 int orc_dense(const OrcCtx *c, const float *vol, int nx, int ny, int nz, const double units[3],
               float *out)
-{ /* SIFT3D_extract_dense_descriptors, dense_rotate == 0 (sift.c:2354-2496) */
+{
+    return orc_dense_ex(c, vol, nx, ny, nz, units, 0, out);
+}
+
+int orc_dense_ex(const OrcCtx *c, const float *vol, int nx, int ny, int nz,
+                 const double units[3], int rotate, float *out)
+{ /* SIFT3D_extract_dense_descriptors (sift.c:2354-2496, rotate: :2521-2588) */
     const long n = (long)nx * ny * nz, ys = nx, zs = (long)nx * ny;
     const float uxf = (float)units[0], uyf = (float)units[1], uzf = (float)units[2];
     const float hist_trunc = k_trunc_thresh * ORC_DESC_NUMEL / 12; /* sift.c:2271 */
@@ -785,6 +841,31 @@ int orc_dense(const OrcCtx *c, const float *vol, int nx, int ny, int nz, const d
     w = orc_gauss_taps(sqrt(c->p.sigma0 * c->p.sigma0 - c->p.sigma_n * c->p.sigma_n), taps, 128);
     orc_blur(vol, sm, nx, ny, nz, 1, units, taps, w, 1.0);
     orc_scale(sm, n);
+
+    if (rotate) { /* extract_dense_descriptors_rotate (sift.c:2521-2588) */
+        const double ori_sigma = c->p.sigma0 * k_ori_sig_fctr;
+        const double desc_sigma = c->p.sigma0 * k_desc_sig_fctr / 4;
+        Level lv;
+        lv.n[0] = nx, lv.n[1] = ny, lv.n[2] = nz;
+        lv.u[0] = units[0], lv.u[1] = units[1], lv.u[2] = units[2];
+        lv.s = 0.0;
+        lv.d = sm;
+#pragma omp parallel for schedule(dynamic)
+        for (z = 0; z < nz; z++) {
+            int x, y;
+            for (y = 0; y < ny; y++)
+                for (x = 0; x < nx; x++) {
+                    const float vc[3] = {(float)x, (float)y, (float)z};
+                    static const float Id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                    float R[9];
+                    const int rej = assign_orientation(&lv, vc, ori_sigma, c->p.corner_thresh, R, NULL);
+                    dense_descrip_rotate(c, &lv, vc, desc_sigma, rej ? Id : R,
+                                         out + 12 * (x + y * ys + z * zs));
+                }
+        }
+        free(sm);
+        goto postproc;
+    }
 
     /* extract_dense_descriptors_no_rotate (sift.c:2429-2496) */
     tmp = (float *)calloc((size_t)n * 12, sizeof(float));
@@ -820,6 +901,7 @@ int orc_dense(const OrcCtx *c, const float *vol, int nx, int ny, int nz, const d
     free(tmp);
     free(sm);
 
+postproc:
     /* postproc_Hist (sift.c:2267-2292), val = raw input intensity (sift.c:2401) */
 #pragma omp parallel for schedule(static)
     for (j = 0; j < n; j++) {

@@ -64,6 +64,9 @@ int orc_describe(const OrcCtx *c, const OrcKeypoint *kp, int n, float *desc, dou
  * out: [z][y][x][12] floats. */
 int orc_dense(const OrcCtx *c, const float *vol, int nx, int ny, int nz, const double units[3],
               float *out);
+/* ... with dense_rotate selectable (rotate = 1: sift.c:2521-2588, :2295-2343) */
+int orc_dense_ex(const OrcCtx *c, const float *vol, int nx, int ny, int nz, const double units[3],
+                 int rotate, float *out);
 
 /* building blocks, exposed for unit tests */
 int orc_gauss_width(double sigma);                      /* imutil.c:3671-3674 */

@@ -149,5 +149,8 @@ int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
 int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out);
 int s3d_k_dense(s3d_engine *e, const float *d_smooth, const float *d_raw, int nx, int ny, int nz,
                 const float inv_units[3], float *d_temp12);
+int s3d_k_dense_rotate(s3d_engine *e, const float *d_smooth, int nx, int ny, int nz,
+                       const float units[3], double ori_sigma, double desc_sigma,
+                       double corner_thresh, float *d_out12);
 int s3d_k_dense_post(s3d_engine *e, float *d_desc12, const float *d_raw, size_t nvox);
 int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx);

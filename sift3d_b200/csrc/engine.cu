@@ -685,6 +685,50 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
     return rc;
 }
 
+int s3d_dense_descriptors_rotate(s3d_engine *e, const float *host_in, int nx, int ny, int nz,
+                                 size_t xs, size_t ys, size_t zs, const double units[3],
+                                 const s3d_filter *smooth, double ori_sigma, double desc_sigma,
+                                 double corner_thresh, float *host_out)
+{
+    DeviceGuard guard(e->device);
+    const size_t n = (size_t)nx * ny * nz;
+    TapSet ts;
+    if (to_tapset(e, smooth, ts)) return -1;
+    float *raw = nullptr, *sm = nullptr, *d12 = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&raw, n * 4) != cudaSuccess || cudaMalloc(&sm, n * 4) != cudaSuccess ||
+            cudaMalloc(&d12, n * 48) != cudaSuccess) {
+            s3d_fail(e, "dense rotate: cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
+            break;
+        }
+        if (upload_strided(e, raw, host_in, nx, ny, nz, xs, ys, zs)) break;
+        // smooth_scale_raw_input (sift.c:1978-2006)
+        const float uf[3] = {(float)(1.0 / units[0]), (float)(1.0 / units[1]), (float)(1.0 / units[2])};
+        if (s3d_k_blur(e, raw, sm, nx, ny, nz, 1, ts, uf)) break;
+        unsigned *mx = e->d_counter ? reinterpret_cast<unsigned *>(e->d_counter + 2) : nullptr;
+        if (s3d_k_max_abs(e, sm, n, mx)) break;
+        if (s3d_k_scale(e, sm, sm, n, mx)) break;
+        // per-voxel orientation + rotated histogram (sift.c:2521-2588)
+        const float fu[3] = {(float)units[0], (float)units[1], (float)units[2]};
+        if (s3d_k_dense_rotate(e, sm, nx, ny, nz, fu, ori_sigma, desc_sigma, corner_thresh, d12))
+            break;
+        if (s3d_k_dense_post(e, d12, raw, n)) break;
+        cudaError_t ce = cudaMemcpyAsync(host_out, d12, n * 48, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) {
+            s3d_fail(e, "dense rotate: download", ce, __FILE__, __LINE__);
+            break;
+        }
+        rc = 0;
+    } while (0);
+    cudaStreamSynchronize(e->stream);
+    if (raw) cudaFree(raw);
+    if (sm) cudaFree(sm);
+    if (d12) cudaFree(d12);
+    return rc;
+}
+
 int s3d_level_download(s3d_engine *e, int which, int o, int s, float *host_dst)
 {
     DeviceGuard guard(e->device);

@@ -226,29 +226,16 @@ __device__ __forceinline__ float expf_glibc(float x, const unsigned long long *t
 }
 
 // ---------------------------------------------------------------- orientation
-// One thread per candidate, accumulating in the reference's raster order so the
-// f32 window gradient and the f64 structure tensor see the same rounding
-// sequence as the CPU (SURVEY.md "Orientation accept/reject flips").  Candidates
-// adjacent in scan order share (o, s) and integer centres, so the lanes of a warp
-// walk identical offsets in lock step.
-__global__ void __launch_bounds__(128)
-    k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
-             double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out)
+// assign_eig_ori + the corner threshold (sift.c:1336-1497) for one window centre, walked in
+// the reference's raster order so the f32 window gradient and the f64 structure tensor see
+// the same rounding sequence as the CPU (SURVEY.md "Orientation accept/reject flips").
+// Returns accept; R is all-zero when the window was rejected before the eigenvectors.
+__device__ __forceinline__ bool orient_core(const float *__restrict__ im, int nx, int ny, int nz,
+                                            float uxf, float uyf, float uzf, float vcx, float vcy,
+                                            float vcz, double sigma, double corner_thresh,
+                                            const unsigned long long *s_tab, float R[9],
+                                            double &conf)
 {
-    __shared__ unsigned long long s_tab[32];
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
-    __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const s3d_keypoint c = kps[i];
-    const int lv = c.o * T.nlev_g + (c.s - T.first_level);
-    const float *__restrict__ im = T.ptrs[lv];
-    const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
-    const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
-    const float vcx = c.x, vcy = c.y, vcz = c.z;
-    // detector: sigma = ori_sig_fctr * key->sd (sift.c:1281); raw API: sigma = key_base.sd
-    // (sift.c:1579)
-    const double sigma = sig_fctr * c.sd;
     const double win_radius = sigma * 3.0;  // ori_rad_fctr, sift.c:1365
     const double r2 = win_radius * win_radius;
     const double s2 = sigma * sigma;
@@ -297,8 +284,9 @@ __global__ void __launch_bounds__(128)
         }
     }
     bool accept = true;
-    double conf = 0.0;
-    float R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    conf = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = 0.0f;
     const float wn2 = fa(fa(fm(wx, wx), fm(wy, wy)), fm(wz, wz));
     if (wn2 < (float)1E-10) accept = false;  // ori_grad_thresh, sift.c:1426
     if (accept) {
@@ -338,6 +326,30 @@ __global__ void __launch_bounds__(128)
             if (corner < corner_thresh) accept = false;  // sift.c:1340-1341
         }
     }
+    return accept;
+}
+
+// One thread per candidate.  Candidates adjacent in scan order share (o, s) and integer
+// centres, so the lanes of a warp walk identical offsets in lock step.
+__global__ void __launch_bounds__(128)
+    k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
+             double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out)
+{
+    __shared__ unsigned long long s_tab[32];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const s3d_keypoint c = kps[i];
+    const int lv = c.o * T.nlev_g + (c.s - T.first_level);
+    // detector: sigma = ori_sig_fctr * key->sd (sift.c:1281); raw API: sigma = key_base.sd
+    // (sift.c:1579)
+    float R[9];
+    double conf;
+    const bool accept =
+        orient_core(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
+                    T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2], c.x, c.y, c.z,
+                    sig_fctr * c.sd, corner_thresh, s_tab, R, conf);
 #pragma unroll
     for (int k = 0; k < 9; k++) kps[i].R[k] = R[k];
     ok[i] = accept ? 1 : 0;
@@ -843,6 +855,100 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// extract_dense_descriptors_rotate (sift.c:2521-2588): per voxel, an orientation from the
+// structure tensor of a sigma0*ori_sig_fctr window (identity when rejected), then one
+// 12-bin histogram of the gradients in a sphere of radius 2*desc_sigma, rotated by R^T
+// (extract_dense_descrip_rotate, sift.c:2295-2343).  One thread per voxel, both windows
+// walked in the reference's raster order, so every f32 sum rounds as on the CPU.
+#define DROT_THREADS 128
+__global__ void __launch_bounds__(DROT_THREADS)
+    k_dense_rotate(const float *__restrict__ sm, int nx, int ny, int nz, float uxf, float uyf,
+                   float uzf, double ori_sigma, double desc_sigma, double corner_thresh,
+                   const MeshDev *__restrict__ M, float *__restrict__ out)
+{
+    __shared__ unsigned long long s_tab[32];
+    __shared__ FaceConst s_face[20];
+    __shared__ int s_lut[32];
+    __shared__ float s_h[12][DROT_THREADS];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+    load_faces(s_face, s_lut, M);
+    __syncthreads();
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t idx = (size_t)blockIdx.x * DROT_THREADS + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % nx);
+    const size_t rr = idx / nx;
+    const int y = (int)(rr % ny);
+    const int z = (int)(rr / ny);
+    const float vcx = (float)x, vcy = (float)y, vcz = (float)z;
+
+    float R[9];
+    double conf;
+    const bool ok = orient_core(sm, nx, ny, nz, uxf, uyf, uzf, vcx, vcy, vcz, ori_sigma,
+                                corner_thresh, s_tab, R, conf);
+    float Rt[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Rt[3 * i + j] = ok ? R[3 * j + i] : (i == j ? 1.0f : 0.0f);
+
+    const float win_radius = (float)__dmul_rn(2.0, desc_sigma);  // desc_rad_fctr, sift.c:2306
+    const float r2 = fm(win_radius, win_radius);
+    const double s2 = __dmul_rn(desc_sigma, desc_sigma);
+    const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
+    int x0, x1, y0, y1, z0, z1;
+    sphere_bounds_f(vcx, win_radius, uxf, nx, x0, x1);
+    sphere_bounds_f(vcy, win_radius, uyf, ny, y0, y1);
+    sphere_bounds_f(vcz, win_radius, uzf, nz, z0, z1);
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    float *h = &s_h[0][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < 12; k++) h[k * DROT_THREADS] = 0.0f;
+
+    for (int zz = z0; zz <= z1; zz++) {
+        const float dz = fm(fs((float)zz, vcz), uzf);
+        const float dz2 = fm(dz, dz);
+        for (int yy = y0; yy <= y1; yy++) {
+            const float dy = fm(fs((float)yy, vcy), uyf);
+            const float dy2 = fm(dy, dy);
+            const float *row = sm + (size_t)yy * ys + (size_t)zz * zs;
+            for (int xx = x0; xx <= x1; xx++) {
+                const float dx = fm(fs((float)xx, vcx), uxf);
+                const float sq = fa(fa(fm(dx, dx), dy2), dz2);
+                if (sq > r2) continue;
+                const float *p = row + xx;
+                float g[3], gr[3], bary[3];
+                g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+                g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+                g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+                    gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
+                const int bin = icos_bin(s_face, s_lut, gr, bary);
+                if (bin < 0) continue;
+                // magnitude of the unrotated gradient (sift.c:2330)
+                const float mag = __fsqrt_rn(fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2])));
+                // sift.c:2333: f32 product, f64 divide by sigma^2, narrowed for expf
+                const float arg = (float)__ddiv_rn((double)fm(-0.5f, sq), s2);
+                const float w = expf_glibc(arg, s_tab);
+                const float mw = fm(mag, w);
+                float *h0 = h + s_face[bin].idx[0] * DROT_THREADS;
+                float *h1 = h + s_face[bin].idx[1] * DROT_THREADS;
+                float *h2 = h + s_face[bin].idx[2] * DROT_THREADS;
+                *h0 = fa(*h0, fm(mw, bary[0]));
+                *h1 = fa(*h1, fm(mw, bary[1]));
+                *h2 = fa(*h2, fm(mw, bary[2]));
+            }
+        }
+    }
+    float4 *o = reinterpret_cast<float4 *>(out + idx * 12);
+    o[0] = make_float4(h[0], h[1 * DROT_THREADS], h[2 * DROT_THREADS], h[3 * DROT_THREADS]);
+    o[1] = make_float4(h[4 * DROT_THREADS], h[5 * DROT_THREADS], h[6 * DROT_THREADS],
+                       h[7 * DROT_THREADS]);
+    o[2] = make_float4(h[8 * DROT_THREADS], h[9 * DROT_THREADS], h[10 * DROT_THREADS],
+                       h[11 * DROT_THREADS]);
+}
+
 // postproc_Hist (sift.c:2267-2292): normalise, clamp, normalise, x intensity
 __global__ void __launch_bounds__(256)
     k_dense_post(float *__restrict__ desc, const float *__restrict__ raw, size_t nvox)
@@ -1023,6 +1129,21 @@ int s3d_k_dense(s3d_engine *e, const float *d_smooth, const float *, int nx, int
     const size_t cap = (size_t)e->num_sms * 16;
     k_dense_bary<<<(int)(want < cap ? want : cap), 256, 0, e->stream>>>(
         d_smooth, nx, ny, nz, inv_units[0], inv_units[1], inv_units[2], e->d_mesh, d_temp12);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_k_dense_rotate(s3d_engine *e, const float *d_smooth, int nx, int ny, int nz,
+                       const float units[3], double ori_sigma, double desc_sigma,
+                       double corner_thresh, float *d_out12)
+{
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t blocks = (total + DROT_THREADS - 1) / DROT_THREADS;
+    if (blocks == 0 || blocks > 0x7fffffffull)
+        return s3d_fail(e, "dense rotate: volume size", cudaSuccess, __FILE__, __LINE__);
+    k_dense_rotate<<<(unsigned)blocks, DROT_THREADS, 0, e->stream>>>(
+        d_smooth, nx, ny, nz, units[0], units[1], units[2], ori_sigma, desc_sigma, corner_thresh,
+        e->d_mesh, d_out12);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

@@ -36,7 +36,10 @@ const char opt_corner_thresh[] = "corner_thresh";
 const char opt_num_kp_levels[] = "num_kp_levels";
 const char opt_sigma_n[] = "sigma_n";
 const char opt_sigma0[] = "sigma0";
+const double ori_sig_fctr = 1.5;   /* sift.c:51 */
+const double ori_rad_fctr = 3.0;   /* sift.c:52 */
 const double desc_sig_fctr = 7.071067812;
+const double desc_rad_fctr = 2.0;  /* sift.c:54 */
 const double gr = 1.6180339887;
 
 #define ERR(...) fprintf(stderr, __VA_ARGS__)
@@ -1020,11 +1023,6 @@ int SIFT3D_extract_dense_descriptors(SIFT3D *const sift3d, const Image *const in
             "only supports single-channel images. \n", in->nc);
         return SIFT3D_FAILURE;
     }
-    if (sift3d->dense_rotate) {
-        ERR("SIFT3D_extract_dense_descriptors: dense_rotate = 1 is not available in the B200 "
-            "build yet (SURVEY.md section 8f, N4) \n");
-        return SIFT3D_FAILURE;
-    }
     if (in->data == NULL || in->nx < 1 || in->ny < 1 || in->nz < 1) return SIFT3D_FAILURE;
     /* resize the output: dims of `in`, 12 channels, default stride; units untouched
      * (sift.c:2375-2380) */
@@ -1042,6 +1040,14 @@ int SIFT3D_extract_dense_descriptors(SIFT3D *const sift3d, const Image *const in
     if ((e = engine_of(sift3d)) == NULL) return SIFT3D_FAILURE;
     if (s3dh_gauss_incremental(&gs, sift3d->gpyr.sigma_n, sift3d->gpyr.sigma0, 3))
         return SIFT3D_FAILURE;
+    if (sift3d->dense_rotate) { /* sift.c:2521-2588 */
+        fs.taps = gs.f.kernel, fs.width = gs.f.width;
+        rc = s3d_dense_descriptors_rotate(e, in->data, in->nx, in->ny, in->nz, in->xs, in->ys,
+                                          in->zs, units, &fs, sift3d->gpyr.sigma0 * ori_sig_fctr,
+                                          sigma_win, sift3d->corner_thresh, desc->data);
+        free(gs.f.kernel);
+        return rc ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
+    }
     if (s3dh_gauss_filter(&gw, sigma_win, 3)) {
         free(gs.f.kernel);
         return SIFT3D_FAILURE;

@@ -50,6 +50,8 @@ class Oracle:
         L.orc_describe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p]
+        L.orc_dense_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_void_p]
         L.orc_gauss_taps.argtypes = [C.c_double, C.c_void_p, C.c_int]
         L.orc_blur.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_int, C.c_double]
@@ -107,12 +109,13 @@ class Oracle:
             raise RuntimeError("orc_describe failed")
         return desc, coords
 
-    def dense(self, vol, units=(1.0, 1.0, 1.0)):
+    def dense(self, vol, units=(1.0, 1.0, 1.0), rotate=False):
         vol = np.ascontiguousarray(vol, np.float32)
         nz, ny, nx = vol.shape
         u = np.asarray(units, np.float64)
         out = np.zeros((nz, ny, nx, 12), np.float32)
-        self.L.orc_dense(self.ctx, vol.ctypes.data, nx, ny, nz, u.ctypes.data, out.ctypes.data)
+        self.L.orc_dense_ex(self.ctx, vol.ctypes.data, nx, ny, nz, u.ctypes.data,
+                            1 if rotate else 0, out.ctypes.data)
         return out
 
     def gauss_taps(self, sigma):

@@ -79,8 +79,28 @@ def run_case(ref, name, vol, units=(1.0, 1.0, 1.0), store_input=True, dense_crop
     print(f"{name}: {vol.shape} units={units} octaves={int(out['noct'])} keypoints={len(kp)}")
 
 
+def run_dense_rotate(ref):
+    """dense_rotate = 1 (sift.c:2521-2588) on two small volumes (the reference is scalar here)."""
+    out = {}
+    cases = {"iso": (blob_volume((48, 52, 44), seed=7)[4:22, 6:26, 3:25], (1.0, 1.0, 1.0)),
+             "aniso": (smooth_noise_volume((18, 20, 22), seed=3), (1.0, 0.8, 1.3))}
+    for key, (vol, units) in cases.items():
+        vol = np.ascontiguousarray(vol, np.float32)
+        with capi.Sift3D(ref) as s:
+            s.s.dense_rotate = 1
+            out[key + "_input"] = vol
+            out[key + "_units"] = np.asarray(units, np.float64)
+            out[key + "_dense"] = s.extract_dense_descriptors(vol, units)
+        print(f"dense_rotate/{key}: {vol.shape} units={units}")
+    np.savez_compressed(HERE / "dense_rotate.npz", **out)
+
+
 def main():
     ref = capi.load_reference()
+    if "--dense-rotate-only" in sys.argv:
+        run_dense_rotate(ref)
+        return
+    run_dense_rotate(ref)
     # 1. synthetic blobs, isotropic, 3 octaves (input regenerated from the seed by the tests)
     run_case(ref, "blob48", blob_volume((48, 52, 44), seed=7),
              dense_crop=(slice(4, 24), slice(6, 24), slice(3, 19)))

@@ -65,6 +65,29 @@ def test_detect_and_describe_match_golden(b200_lib, name):
             assert err <= 1e-5, err
 
 
+def test_dense_rotate_matches_golden_and_oracle(b200_lib, oracle_cls):
+    """SIFT3D_extract_dense_descriptors with dense_rotate = 1 (sift.c:2521-2588): golden
+    vectors from the compiled reference, then a fresh volume against the oracle."""
+    from conftest import GOLDEN
+    from sift3d_b200 import capi
+    from sift3d_b200.volumes import smooth_noise_volume
+    z = np.load(GOLDEN / "dense_rotate.npz")
+    with capi.Sift3D(b200_lib) as s:
+        s.s.dense_rotate = 1
+        for key in ("iso", "aniso"):
+            vol, units, want = z[key + "_input"], tuple(z[key + "_units"]), z[key + "_dense"]
+            got = s.extract_dense_descriptors(vol, units)
+            assert got.shape == want.shape
+            err = np.abs(got - want).max() / np.abs(want).max()
+            assert err <= 1e-6, (key, err)   # every f32 sum is in the reference's order
+        vol = smooth_noise_volume((40, 36, 44), seed=21)
+        units = (0.9, 1.0, 1.2)
+        got = s.extract_dense_descriptors(vol, units)
+    want = oracle_cls().dense(vol, units, rotate=True)
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err <= 1e-6, err
+
+
 def test_same_calls_two_libraries(b200_lib, ref_lib):
     """The reference's own self-consistency style (Sift3DTest.m detect/extract tests):
     identical calls on the reference library and on the B200 library."""

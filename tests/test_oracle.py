@@ -47,6 +47,20 @@ def test_oracle_matches_golden(oracle_cls, name):
         assert np.abs(dd - g["dense"]).max() <= 1e-6 * max(1.0, np.abs(g["dense"]).max())
 
 
+def test_oracle_dense_rotate_matches_golden(oracle_cls):
+    """dense_rotate = 1 (sift.c:2521-2588): per-voxel orientation + rotated histogram."""
+    from conftest import GOLDEN
+    z = np.load(GOLDEN / "dense_rotate.npz")
+    orc = oracle_cls()
+    for key in ("iso", "aniso"):
+        vol, units, want = z[key + "_input"], tuple(z[key + "_units"]), z[key + "_dense"]
+        got = orc.dense(vol, units, rotate=True)
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), np.abs(got - want).max()
+        # the rotation matters: the no-rotate path gives a different field
+        assert np.abs(orc.dense(vol, units) - want).max() > 1e-3
+
+
 def test_oracle_matches_compiled_reference(oracle_cls, ref_lib):
     """Same calls on the reference library and on the restatement, fresh random input."""
     from sift3d_b200 import capi
