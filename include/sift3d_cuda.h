@@ -139,6 +139,46 @@ int s3d_level_download(s3d_engine *e, int which, int o, int s, float *host_dst);
 int s3d_pyramid_copy(s3d_engine *dst, const s3d_engine *src); /* copy_Pyramid, imutil.c:3995 */
 int s3d_num_octaves(const s3d_engine *e);
 
+/* ---- Z-slab tiling of ONE volume over several GPUs (BASELINE.json configs[4]) ------
+ * No reference counterpart (the reference is one process in host memory); the contract is
+ * its RESULT on the whole volume: identical pyramid bits, keypoints (order included) and
+ * descriptors.  Rank r owns the octave-0 planes [zsplit[r], zsplit[r+1]) and, per octave,
+ * the planes whose 2x-decimation source it owns (im_downsample_2x, imutil.c:1742-1768).
+ * Communication: all-reduce(max) of max|image| (im_scale, imutil.c:1983) and max|DoG|
+ * (sift.c:1161-1169), and halo planes of every Gaussian level (convolve_sep_gen z reach,
+ * imutil.c:2274-2393; the orientation/descriptor windows, sift.c:1354, :1834). */
+typedef struct s3d_comm s3d_comm;
+/* in-process transport: one host thread per rank (any mix of devices, incl. all on one) */
+void *s3d_local_world_create(int nranks);
+void s3d_local_world_destroy(void *world);
+int s3d_comm_create_local(s3d_comm **out, void *world, int rank, int device);
+/* NCCL transport: one process per GPU; rank 0 creates the id and the caller broadcasts it
+ * (e.g. torch.distributed); libnccl.so.2 is dlopen'ed ($SIFT3D_NCCL_LIB overrides) */
+int s3d_nccl_unique_id(unsigned char id[128]);
+int s3d_comm_create_nccl(s3d_comm **out, int rank, int nranks, const unsigned char id[128],
+                         int device);
+void s3d_comm_destroy(s3d_comm *c);
+int s3d_comm_rank(const s3d_comm *c);
+int s3d_comm_size(const s3d_comm *c);
+const char *s3d_comm_error(const s3d_comm *c);
+int s3d_comm_allreduce_max_u32(s3d_comm *c, s3d_engine *e, unsigned *dev, int n);
+/* Host logic: planes owned per rank and octave, own[(r*num_octaves + o)*2 + {0,1}]. */
+int s3d_slab_plan(int nranks, int num_octaves, int nz0, const int *zsplit, int *own);
+/* Host logic: halo transfers of one level of octave o (NZ planes) for halo width h, as rows
+ * {kind: 0 send / 1 recv, peer, z0, z1} in the order both ends of a pair use. */
+int s3d_slab_halo_plan(int nranks, int num_octaves, const int *own, int o, int NZ, int h, int rank,
+                       int *out, int cap);
+/* Like s3d_pyramid_resize, with the GLOBAL level geometry; call s3d_pyramid_filters first.
+ * Afterwards s3d_build_pyramid / s3d_detect_extrema / s3d_assign_orientations /
+ * s3d_extract_descriptors work on the slab; keypoint coordinates are global. */
+int s3d_slab_pyramid_resize(s3d_engine *e, s3d_comm *comm, int num_octaves, int num_kp_levels,
+                            const s3d_geom *gpyr, const s3d_geom *dog, const int *zsplit);
+/* The rank's owned planes of the input, nx*ny*(zsplit[r+1]-zsplit[r]) voxels. */
+int s3d_slab_image_upload(s3d_engine *e, const float *host, size_t xs, size_t ys, size_t zs);
+int s3d_slab_image_from_device(s3d_engine *e, const float *dev);
+/* info = {own0, own1, lo, hi, NZ, halo} of octave o: owned planes, planes held, global count. */
+int s3d_slab_info(const s3d_engine *e, int o, int info[6]);
+
 /* ---- kernel-level entry (tests / bench roofline): device pointers ------------ */
 /* apply_Sep_FIR_filter (imutil.c:3459): x, y, z passes, nc interleaved channels. */
 int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx, int ny, int nz,

@@ -442,22 +442,36 @@ bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps,
     return true;
 }
 
+int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                          const TapSet &taps, int zb, int ze);
+
 int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
                    const TapSet &taps, const float uf[3])
 {
     (void)uf;
+    return s3d_blur_fused_zrange(e, src, dst, nx, ny, nz, taps, 0, nz);
+}
+
+// Output planes [zb, ze) only (Z-slab tiling: the planes outside are halo, filled by the
+// neighbours).  The z mirror rules key on plane 0 / nz-1 of the buffer, which a tiled caller
+// arranges to be true volume ends or out of the filter's reach.
+int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                          const TapSet &taps, int zb, int ze)
+{
     const int hw = taps.width / 2;
+    const int nzr = ze - zb;
+    if (nzr <= 0) return 0;
     // ---- work decomposition: columns (overlapping last tile) x balanced z ranges,
     //      computed once per volume size and cached in the engine -------------------------
     const SegTab *tab = nullptr;
     for (const auto &t : e->segtabs)
-        if (t.nx == nx && t.ny == ny && t.nz == nz) tab = &t;
+        if (t.nx == nx && t.ny == ny && t.nz == nz && t.zb == zb && t.ze == ze) tab = &t;
     if (!tab) {
         std::vector<int> xs, ys;
         for (int x = 0; x < nx; x += TX) xs.push_back(std::min(x, nx - TX));
         for (int y = 0; y < ny; y += TY) ys.push_back(std::min(y, ny - TY));
         const long ncol = (long)xs.size() * ys.size();
-        const long total = ncol * nz;
+        const long total = ncol * nzr;
         const int grid = (int)std::min<long>(e->num_sms, std::max<long>(1, total / 16));
         // Edge columns cost more per plane (mirror samples are synthesised by a few threads on the
         // critical path of every step); measured on B200 (tools/blur_dbg.py, cycles/step relative
@@ -473,23 +487,23 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
             if (y0 - hw < 0) w *= e->blur_w[2];
             if (y0 + TY + hw > ny - 1) w *= e->blur_w[3];
             wcol[c] = w;
-            wsum += w * nz;
+            wsum += w * nzr;
         }
         std::vector<Seg> segs;
         std::vector<int> start(grid + 1, 0);
         {
             const double quota = wsum / grid;
             long col = 0;
-            int z = 0;
+            int z = zb;
             for (int b = 0; b < grid; b++) {
                 start[b] = (int)segs.size();
                 double need = quota;
                 while (col < ncol && (need > 1e-9 || b == grid - 1)) {
-                    const double per = wcol[col] + 2.0 * hw * wcol[col] / std::max(nz, 1) * 0;  // halo ignored
-                    int take = (b == grid - 1) ? nz - z : (int)std::min<double>(nz - z, std::ceil(need / per - 1e-9));
+                    const double per = wcol[col];  // halo planes ignored
+                    int take = (b == grid - 1) ? ze - z : (int)std::min<double>(ze - z, std::ceil(need / per - 1e-9));
                     if (take <= 0) break;
                     // avoid leaving a sliver shorter than the halo at the end of a column
-                    if (nz - (z + take) > 0 && nz - (z + take) < 2 * hw && b != grid - 1) take = nz - z;
+                    if (ze - (z + take) > 0 && ze - (z + take) < 2 * hw && b != grid - 1) take = ze - z;
                     Seg sg;
                     sg.x0 = xs[col % xs.size()];
                     sg.y0 = ys[col / xs.size()];
@@ -498,8 +512,8 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
                     segs.push_back(sg);
                     need -= take * per;
                     z += take;
-                    if (z >= nz) {
-                        z = 0;
+                    if (z >= ze) {
+                        z = zb;
                         col++;
                     }
                 }
@@ -512,6 +526,7 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
         memcpy(host.data() + segs.size() * sizeof(Seg), start.data(), start.size() * sizeof(int));
         SegTab nt;
         nt.nx = nx, nt.ny = ny, nt.nz = nz, nt.grid = grid, nt.nseg = segs.size(), nt.d = nullptr;
+        nt.zb = zb, nt.ze = ze;
         S3D_CUDA(e, cudaMalloc(&nt.d, need));
         S3D_CUDA(e, cudaMemcpyAsync(nt.d, host.data(), need, cudaMemcpyHostToDevice, e->stream));
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));

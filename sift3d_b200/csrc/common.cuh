@@ -47,11 +47,21 @@ struct MeshDev {
     float vert[12][3];  // unit vertex directions (fast-path preselection only)
 };
 
-struct SegTab {  // cached work decomposition of the fused blur for one volume size
+struct SegTab {  // cached work decomposition of the fused blur for one volume size / z range
     int nx, ny, nz, grid;
+    int zb, ze;  // output planes [zb, ze) (0, nz for a whole volume)
     void *d;
     size_t nseg;
 };
+
+// Z-slab tiling (slab.cu): the planes of one octave this rank owns / holds.
+struct SlabOct {
+    int NZ = 0;          // global plane count of the octave
+    int own0 = 0, own1 = 0;  // owned planes [own0, own1), global indices
+    int lo = 0, hi = 0;      // planes held locally [lo, hi) = owned + halo, clipped to [0, NZ)
+};
+
+struct s3d_comm;  // slab.cu
 
 struct s3d_engine {
     int device = 0;
@@ -104,6 +114,16 @@ struct s3d_engine {
     unsigned char *d_desc = nullptr;
     size_t desc_cap = 0;
 
+    // Z-slab tiling: empty `slab` = the engine holds whole volumes
+    s3d_comm *comm = nullptr;        // not owned
+    std::vector<SlabOct> slab;       // per octave
+    std::vector<int> zsplit;         // octave-0 plane split over the ranks (nranks + 1 entries)
+    std::vector<int> slab_own;       // [rank][octave] -> own0, own1 of every rank
+    std::vector<int> slab_need;      // [octave][gpyr level] -> halo planes its consumers read
+    std::vector<s3d_geom> slab_g;    // global geometry of the Gaussian levels
+    int slab_halo = 0;               // halo planes kept around the owned range of every level
+    int *d_level_zoff = nullptr;     // per gpyr level: global z of local plane 0 (0 when not tiled)
+
     std::vector<SegTab> segtabs;
     long long *d_blur_dbg = nullptr;  // debug: per-CTA clocks of the last fused blur
 
@@ -116,6 +136,7 @@ struct s3d_engine {
 };
 
 int s3d_fail(s3d_engine *e, const char *what, cudaError_t ce, const char *file, int line);
+void s3d_free_pyramid(s3d_engine *e);
 
 #define S3D_CUDA(e, call)                                                     \
     do {                                                                      \
@@ -135,11 +156,20 @@ int s3d_k_max_abs(s3d_engine *e, const float *x, size_t n, unsigned *d_bits);
 int s3d_k_scale(s3d_engine *e, const float *src, float *dst, size_t n, const unsigned *d_bits);
 int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz, int nc,
                const TapSet &taps, const float uf[3]);
+// same, output restricted to planes [zb, ze) (src planes within the filter's z reach of that
+// range must be valid; mirrors apply at plane 0 / nz-1 only, i.e. at true volume ends)
+int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                      const TapSet &taps, const float uf[3], int zb, int ze);
+// planes beyond an output plane that a z pass with these taps reads (incl. the lerp partner)
+int s3d_blur_z_reach(const TapSet &taps, float ufz);
 int s3d_k_decimate(s3d_engine *e, const float *src, int sx, int sy, int sz, float *dst, int dx,
                    int dy, int dz);
 int s3d_k_dog(s3d_engine *e, const float *a, const float *b, float *d, size_t n,
               unsigned *d_maxbits);
 int s3d_k_extrema_octave(s3d_engine *e, int o, float peak_thresh_dummy, double peak_thresh);
+// scan only local planes [zl0, zl0 + nzs) of the octave's DoG buffers as if they were a whole
+// volume (its first and last plane are neighbours only); emitted z = local-sub z + zbase
+int s3d_k_extrema_range(s3d_engine *e, int o, double peak_thresh, int zl0, int nzs, int zbase);
 int s3d_ensure_scratch(s3d_engine *e, size_t elems);
 
 // ---- launchers implemented in keypoint.cu -----------------------------------

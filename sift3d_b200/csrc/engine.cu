@@ -24,6 +24,37 @@ int s3d_fail(s3d_engine *e, const char *what, cudaError_t ce, const char *file, 
 }
 
 int s3d_pack_candidates(s3d_engine *e, s3d_keypoint *d_out);  // keypoint.cu
+int s3d_slab_build_pyramid(s3d_engine *e);                     // slab.cu
+int s3d_slab_extrema_octave(s3d_engine *e, int o, double peak_thresh);
+
+void s3d_free_pyramid(s3d_engine *e)
+{
+    for (auto &l : e->g)
+        if (l.d) cudaFree(l.d);
+    for (auto &l : e->dog)
+        if (l.d) cudaFree(l.d);
+    e->g.clear();
+    e->dog.clear();
+    if (e->d_level_ptrs) cudaFree(e->d_level_ptrs);
+    if (e->d_level_dims) cudaFree(e->d_level_dims);
+    if (e->d_level_units) cudaFree(e->d_level_units);
+    if (e->d_level_scales) cudaFree(e->d_level_scales);
+    if (e->d_level_zoff) cudaFree(e->d_level_zoff);
+    if (e->d_scalars) cudaFree(e->d_scalars);
+    e->d_level_ptrs = nullptr;
+    e->d_level_dims = nullptr;
+    e->d_level_units = nullptr;
+    e->d_level_scales = nullptr;
+    e->d_level_zoff = nullptr;
+    e->d_scalars = nullptr;
+    e->noct = 0;
+    e->slab.clear();
+    e->slab_own.clear();
+    e->slab_need.clear();
+    e->slab_g.clear();
+    e->zsplit.clear();
+    e->comm = nullptr;
+}
 
 namespace {
 
@@ -42,26 +73,7 @@ struct DeviceGuard {
     }
 };
 
-void free_pyramid(s3d_engine *e)
-{
-    for (auto &l : e->g)
-        if (l.d) cudaFree(l.d);
-    for (auto &l : e->dog)
-        if (l.d) cudaFree(l.d);
-    e->g.clear();
-    e->dog.clear();
-    if (e->d_level_ptrs) cudaFree(e->d_level_ptrs);
-    if (e->d_level_dims) cudaFree(e->d_level_dims);
-    if (e->d_level_units) cudaFree(e->d_level_units);
-    if (e->d_level_scales) cudaFree(e->d_level_scales);
-    if (e->d_scalars) cudaFree(e->d_scalars);
-    e->d_level_ptrs = nullptr;
-    e->d_level_dims = nullptr;
-    e->d_level_units = nullptr;
-    e->d_level_scales = nullptr;
-    e->d_scalars = nullptr;
-    e->noct = 0;
-}
+void free_pyramid(s3d_engine *e) { s3d_free_pyramid(e); }
 
 int ensure_cand(s3d_engine *e, int cap)
 {
@@ -233,7 +245,7 @@ int s3d_pyramid_resize(s3d_engine *e, int num_octaves, int num_kp_levels, const 
     S3D_CUDA(e, cudaStreamSynchronize(e->stream));
     const int nlev_d = num_kp_levels + 2, nlev_g = num_kp_levels + 3;
     // keep the allocation when nothing changed
-    bool same = e->noct == num_octaves && e->K == num_kp_levels &&
+    bool same = e->slab.empty() && e->noct == num_octaves && e->K == num_kp_levels &&
                 (int)e->g.size() == num_octaves * nlev_g;
     for (int i = 0; same && i < num_octaves * nlev_g; i++)
         same = e->g[i].g.nx == gpyr[i].nx && e->g[i].g.ny == gpyr[i].ny && e->g[i].g.nz == gpyr[i].nz;
@@ -367,6 +379,7 @@ int s3d_build_pyramid(s3d_engine *e)
     if (e->noct < 1 || !e->im || (int)e->oct_taps.size() != e->nlev_g - 1)
         return s3d_fail(e, "s3d_build_pyramid: pyramid/filters/image not configured", cudaSuccess,
                         __FILE__, __LINE__);
+    if (!e->slab.empty()) return s3d_slab_build_pyramid(e);
     const LevelDev &base = e->g[0];
     if (base.g.nx != e->im_nx || base.g.ny != e->im_ny || base.g.nz != e->im_nz)
         return s3d_fail(e, "s3d_build_pyramid: image/pyramid size mismatch", cudaSuccess, __FILE__,
@@ -422,7 +435,9 @@ int s3d_detect_extrema(s3d_engine *e, double peak_thresh, int *num_candidates)
         if (ensure_cand(e, want_cap)) return -1;
         S3D_CUDA(e, cudaMemsetAsync(e->d_counter, 0, 4 * sizeof(int), e->stream));
         for (int o = 0; o < e->noct; o++)
-            if (s3d_k_extrema_octave(e, o, 0.0f, peak_thresh)) return -1;
+            if (e->slab.empty() ? s3d_k_extrema_octave(e, o, 0.0f, peak_thresh)
+                                : s3d_slab_extrema_octave(e, o, peak_thresh))
+                return -1;
         int total = 0;
         S3D_CUDA(e, cudaMemcpyAsync(&total, e->d_counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));

@@ -171,7 +171,16 @@ struct PyrTable {
     const double *scales;
     int nlev_g;
     int first_level;
+    const int *zoff;  // Z-slab tiling: global z of local plane 0, per level (nullptr: whole volumes)
 };
+
+// Keypoint z coordinates are global; the level buffers of a Z-slab engine start at plane
+// zoff.  The difference of two integer-valued floats is exact, and every later use of the
+// centre is relative (voxel - centre), so tiled and untiled runs see identical arithmetic.
+__device__ __forceinline__ float local_z(const PyrTable &T, int lv, float z)
+{
+    return T.zoff ? __fsub_rn(z, (float)T.zoff[lv]) : z;
+}
 
 // IM_LOOP_SPHERE_START bounds (sift.c:96-119) with a double radius
 __device__ __forceinline__ void sphere_bounds_d(float c, double rad, float uf, int n, int &lo,
@@ -348,8 +357,8 @@ __global__ void __launch_bounds__(128)
     double conf;
     const bool accept =
         orient_core(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
-                    T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2], c.x, c.y, c.z,
-                    sig_fctr * c.sd, corner_thresh, s_tab, R, conf);
+                    T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2], c.x, c.y,
+                    local_z(T, lv, c.z), sig_fctr * c.sd, corner_thresh, s_tab, R, conf);
 #pragma unroll
     for (int k = 0; k < 9; k++) kps[i].R[k] = R[k];
     ok[i] = accept ? 1 : 0;
@@ -442,8 +451,10 @@ __global__ void __launch_bounds__(DESC_THREADS)
     if (ki >= n) return;
     if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
     load_faces(s_face, s_lut, M);
-    const s3d_keypoint kp = kps[ki];
+    s3d_keypoint kp = kps[ki];
     const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
+    const float z_global = kp.z;
+    kp.z = local_z(T, lv, kp.z);
     const float *__restrict__ im = T.ptrs[lv];
     const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
     const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
@@ -573,7 +584,7 @@ __global__ void __launch_bounds__(DESC_THREADS)
         const double f = ldexp(1.0, kp.o);  // sift.c:1851, 1922-1925
         o64[0] = (double)kp.x * f;
         o64[1] = (double)kp.y * f;
-        o64[2] = (double)kp.z * f;
+        o64[2] = (double)z_global * f;
         o64[3] = kp.sd;
     }
 }
@@ -608,8 +619,10 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
     const int ki = blockIdx.x;
     if (ki >= n) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const s3d_keypoint kp = kps[ki];
+    s3d_keypoint kp = kps[ki];
     const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
+    const float z_global = kp.z;
+    kp.z = local_z(T, lv, kp.z);
     const float *__restrict__ im = T.ptrs[lv];
     const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
     const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
@@ -805,7 +818,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
         const double f = ldexp(1.0, kp.o);  // sift.c:1851, 1922-1925
         o64[0] = (double)kp.x * f;
         o64[1] = (double)kp.y * f;
-        o64[2] = (double)kp.z * f;
+        o64[2] = (double)z_global * f;
         o64[3] = kp.sd;
     }
 }
@@ -990,6 +1003,7 @@ PyrTable make_table(const s3d_engine *e)
     T.scales = e->d_level_scales;
     T.nlev_g = e->nlev_g;
     T.first_level = e->first_level;
+    T.zoff = e->slab.empty() ? nullptr : e->d_level_zoff;
     return T;
 }
 

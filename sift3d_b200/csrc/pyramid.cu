@@ -12,6 +12,7 @@
 // with one IEEE rounding per (*) and (+), taps visited d = -hw..hw.  No FMA.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -25,19 +26,23 @@ __device__ __forceinline__ float warp_max(float v)
 }
 
 // ---------------------------------------------------------------- max |x|
+// The flat kernels below take `head` = number of leading elements before the first 16-byte
+// boundary (plane ranges of a Z-slab start at arbitrary element offsets): scalar head,
+// float4 body, scalar tail.
 __global__ void __launch_bounds__(256) k_max_abs(const float *__restrict__ x, size_t n,
-                                                 unsigned *__restrict__ out_bits)
+                                                 size_t head, unsigned *__restrict__ out_bits)
 {
     float m = 0.0f;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
-    const size_t n4 = n / 4;
-    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    const size_t n4 = (n - head) / 4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x + head);
     for (size_t i = tid; i < n4; i += nth) {
         const float4 v = __ldg(x4 + i);
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    for (size_t i = n4 * 4 + tid; i < n; i += nth) m = fmaxf(m, fabsf(x[i]));
+    for (size_t i = tid; i < head; i += nth) m = fmaxf(m, fabsf(x[i]));
+    for (size_t i = head + n4 * 4 + tid; i < n; i += nth) m = fmaxf(m, fabsf(x[i]));
     m = warp_max(m);
     __shared__ float sm[8];
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
@@ -52,21 +57,23 @@ __global__ void __launch_bounds__(256) k_max_abs(const float *__restrict__ x, si
 
 // ---------------------------------------------------------------- x / max
 __global__ void __launch_bounds__(256) k_scale(const float *__restrict__ src,
-                                               float *__restrict__ dst, size_t n,
+                                               float *__restrict__ dst, size_t n, size_t head,
                                                const unsigned *__restrict__ max_bits)
 {
     const float mx = __uint_as_float(*max_bits);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
-    const size_t n4 = n / 4;
-    const float4 *s4 = reinterpret_cast<const float4 *>(src);
-    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    const size_t n4 = (n - head) / 4;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src + head);
+    float4 *d4 = reinterpret_cast<float4 *>(dst + head);
     if (mx == 0.0f) {  // im_scale returns early (imutil.c:1984-1985)
         if (src == dst) return;
         for (size_t i = tid; i < n4; i += nth) d4[i] = s4[i];
-        for (size_t i = n4 * 4 + tid; i < n; i += nth) dst[i] = src[i];
+        for (size_t i = tid; i < head; i += nth) dst[i] = src[i];
+        for (size_t i = head + n4 * 4 + tid; i < n; i += nth) dst[i] = src[i];
         return;
     }
+    for (size_t i = tid; i < head; i += nth) dst[i] = __fdiv_rn(src[i], mx);
     for (size_t i = tid; i < n4; i += nth) {
         float4 v = s4[i];
         v.x = __fdiv_rn(v.x, mx);
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(256) k_scale(const float *__restrict__ src,
         v.w = __fdiv_rn(v.w, mx);
         d4[i] = v;
     }
-    for (size_t i = n4 * 4 + tid; i < n; i += nth) dst[i] = __fdiv_rn(src[i], mx);
+    for (size_t i = head + n4 * 4 + tid; i < n; i += nth) dst[i] = __fdiv_rn(src[i], mx);
 }
 
 // ---------------------------------------------------------------- generic 1-axis FIR
@@ -96,13 +103,16 @@ __device__ __forceinline__ float samp_acc(float acc, float tap, float c, const f
     return __fadd_rn(acc, __fmul_rn(tap, v));
 }
 
+// For AXIS == 2 the launch may cover only the output planes [zoff, zoff + nz) of a line that
+// is nfull planes long: `src` is the base of the whole buffer, `dst` points at plane zoff.
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src,
                                                    float *__restrict__ dst, int nx, int ny,
-                                                   int nz, int nc, const TapSet taps, float uf)
+                                                   int nz, int nc, const TapSet taps, float uf,
+                                                   int zoff, int nfull)
 {
     const size_t total = (size_t)nx * ny * nz * nc;
-    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nz);
+    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nfull);
     const size_t st = AXIS == 0 ? (size_t)nc : (AXIS == 1 ? (size_t)nc * nx : (size_t)nc * nx * ny);
     const int hw = taps.width / 2;
     const int dim_end = n - 1;
@@ -116,8 +126,8 @@ __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src
         r /= nx;
         const int y = (int)(r % ny);
         const int z = (int)(r / ny);
-        const int i = AXIS == 0 ? x : (AXIS == 1 ? y : z);
-        const float *line = src + (idx - (size_t)i * st);
+        const int i = AXIS == 0 ? x : (AXIS == 1 ? y : z + zoff);
+        const float *line = src + (idx - (size_t)(AXIS == 2 ? z : i) * st);
         float acc = 0.0f;
         if (i >= start && i <= end) {
             float c = (float)i;  // carried across taps (imutil.c:2335-2350)
@@ -160,15 +170,21 @@ __global__ void __launch_bounds__(256) k_decimate(const float *__restrict__ src,
 // ---------------------------------------------------------------- DoG + max|DoG|
 __global__ void __launch_bounds__(256) k_dog(const float *__restrict__ a,
                                              const float *__restrict__ b, float *__restrict__ d,
-                                             size_t n, unsigned *__restrict__ max_bits)
+                                             size_t n, size_t head,
+                                             unsigned *__restrict__ max_bits)
 {
     float m = 0.0f;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
-    const size_t n4 = n / 4;
-    const float4 *a4 = reinterpret_cast<const float4 *>(a);
-    const float4 *b4 = reinterpret_cast<const float4 *>(b);
-    float4 *d4 = reinterpret_cast<float4 *>(d);
+    const size_t n4 = (n - head) / 4;
+    const float4 *a4 = reinterpret_cast<const float4 *>(a + head);
+    const float4 *b4 = reinterpret_cast<const float4 *>(b + head);
+    float4 *d4 = reinterpret_cast<float4 *>(d + head);
+    for (size_t i = tid; i < head; i += nth) {
+        const float v = __fsub_rn(a[i], b[i]);
+        d[i] = v;
+        m = fmaxf(m, fabsf(v));
+    }
     for (size_t i = tid; i < n4; i += nth) {
         const float4 va = __ldg(a4 + i), vb = __ldg(b4 + i);
         float4 v;
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(256) k_dog(const float *__restrict__ a,
         d4[i] = v;
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    for (size_t i = n4 * 4 + tid; i < n; i += nth) {
+    for (size_t i = head + n4 * 4 + tid; i < n; i += nth) {
         const float v = __fsub_rn(a[i], b[i]);
         d[i] = v;
         m = fmaxf(m, fabsf(v));
@@ -300,7 +316,7 @@ __global__ void __launch_bounds__(1024) k_extrema_scan(int *__restrict__ blockcn
 // Pass C: ordered scatter of the marked voxels.
 __global__ void __launch_bounds__(EXT_BLOCK)
     k_extrema_emit(const unsigned *__restrict__ mask, const int *__restrict__ blockoff, int nblocks,
-                   size_t words_per_level, int K, int o, int nx, int ny, int nz,
+                   size_t words_per_level, int K, int o, int nx, int ny, int nz, int zbase,
                    Candidate *__restrict__ cand, int cap)
 {
     const size_t total = (size_t)nx * ny * nz;
@@ -333,12 +349,20 @@ __global__ void __launch_bounds__(EXT_BLOCK)
                 c.x = (int)(idx % nx);
                 const size_t r = idx / nx;
                 c.y = (int)(r % ny);
-                c.z = (int)(r / ny);
+                c.z = (int)(r / ny) + zbase;
                 cand[pos] = c;
             }
         }
         __syncthreads();
     }
+}
+
+// leading scalars before a common 16-byte boundary; n (all scalar) if the pointers disagree
+inline size_t head_of(size_t n, const void *a, const void *b = nullptr, const void *c = nullptr)
+{
+    const size_t ma = (size_t)((uintptr_t)a & 15);
+    if ((b && ((uintptr_t)b & 15) != ma) || (c && ((uintptr_t)c & 15) != ma) || (ma & 3)) return n;
+    return std::min(n, ((16 - ma) & 15) / 4);
 }
 
 inline int grid_for(const s3d_engine *e, size_t work_items, int block, int per_sm)
@@ -353,14 +377,15 @@ inline int grid_for(const s3d_engine *e, size_t work_items, int block, int per_s
 int s3d_k_max_abs(s3d_engine *e, const float *x, size_t n, unsigned *d_bits)
 {
     S3D_CUDA(e, cudaMemsetAsync(d_bits, 0, sizeof(unsigned), e->stream));
-    k_max_abs<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(x, n, d_bits);
+    k_max_abs<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(x, n, head_of(n, x), d_bits);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
 
 int s3d_k_scale(s3d_engine *e, const float *src, float *dst, size_t n, const unsigned *d_bits)
 {
-    k_scale<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(src, dst, n, d_bits);
+    k_scale<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(src, dst, n,
+                                                                   head_of(n, src, dst), d_bits);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -391,12 +416,49 @@ int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int 
     const size_t total = (size_t)nx * ny * nz * nc;
     if (s3d_ensure_scratch(e, total)) return -1;
     const int grid = grid_for(e, total, 256, 16);
-    k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0]);
+    k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0],
+                                               0, nz);
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
-                                               taps, uf[1]);
+                                               taps, uf[1], 0, nz);
     S3D_LAUNCH_CHECK(e);
-    k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2]);
+    k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2],
+                                               0, nz);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+int s3d_blur_z_reach(const TapSet &taps, float ufz)
+{  // samples reach c = i +- hw*uf, read as the pair (floor(c), floor(c) + 1)
+    return (int)ceilf((float)(taps.width / 2) * ufz) + 1;
+}
+
+int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                          const TapSet &taps, int zb, int ze);  // blur_fused.cu
+
+int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
+                      const TapSet &taps, const float uf[3], int zb, int ze)
+{
+    if (ze <= zb) return 0;
+    if (e->blur_mode == 0 && s3d_blur_fused_eligible(nx, ny, nz, 1, taps, uf))
+        return s3d_blur_fused_zrange(e, src, dst, nx, ny, nz, taps, zb, ze);
+    // x and y passes on the planes the z pass will read, then the z pass on [zb, ze).  The
+    // scratch volumes hold planes [p0, p1) only; p0 == 0 / p1 == nz exactly when the range
+    // touches a true end of the line, so the mirror rules see the right geometry.
+    const int h = s3d_blur_z_reach(taps, uf[2]);
+    const int p0 = std::max(0, zb - h), p1 = std::min(nz, ze + h);
+    const size_t plane = (size_t)nx * ny;
+    const size_t sub = plane * (size_t)(p1 - p0);
+    if (s3d_ensure_scratch(e, sub)) return -1;
+    const int grid = grid_for(e, sub, 256, 16);
+    k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src + plane * p0, e->scratch[0], nx, ny, p1 - p0, 1,
+                                               taps, uf[0], 0, p1 - p0);
+    S3D_LAUNCH_CHECK(e);
+    k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, p1 - p0, 1,
+                                               taps, uf[1], 0, p1 - p0);
+    S3D_LAUNCH_CHECK(e);
+    k_conv_axis<2><<<grid_for(e, plane * (size_t)(ze - zb), 256, 16), 256, 0, e->stream>>>(
+        e->scratch[1], dst + plane * zb, nx, ny, ze - zb, 1, taps, uf[2], zb - p0, p1 - p0);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -414,15 +476,22 @@ int s3d_k_decimate(s3d_engine *e, const float *src, int sx, int sy, int sz, floa
 int s3d_k_dog(s3d_engine *e, const float *a, const float *b, float *d, size_t n,
               unsigned *d_maxbits)
 {
-    k_dog<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(a, b, d, n, d_maxbits);
+    k_dog<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(a, b, d, n, head_of(n, a, b, d),
+                                                                 d_maxbits);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
 
 int s3d_k_extrema_octave(s3d_engine *e, int o, float, double peak_thresh)
 {
+    return s3d_k_extrema_range(e, o, peak_thresh, 0, e->dog[(size_t)o * e->nlev_d].g.nz, 0);
+}
+
+int s3d_k_extrema_range(s3d_engine *e, int o, double peak_thresh, int zl0, int nzs, int zbase)
+{
     const LevelDev &l0 = e->dog[(size_t)o * e->nlev_d];
-    const int nx = l0.g.nx, ny = l0.g.ny, nz = l0.g.nz;
+    const int nx = l0.g.nx, ny = l0.g.ny, nz = nzs;
+    const size_t zskip = (size_t)nx * ny * zl0;
     const size_t total = (size_t)nx * ny * nz;
     const int nblocks = (int)((total + EXT_BLOCK - 1) / EXT_BLOCK);
     const size_t words = (size_t)nblocks * (EXT_BLOCK / 32);
@@ -443,7 +512,7 @@ int s3d_k_extrema_octave(s3d_engine *e, int o, float, double peak_thresh)
         e->blockcnt_cap = (size_t)nblocks * K;
     }
     ExtLevels L;
-    for (int s = -1; s <= K; s++) L.dog[s + 1] = e->dog[(size_t)o * e->nlev_d + (s + 1)].d;
+    for (int s = -1; s <= K; s++) L.dog[s + 1] = e->dog[(size_t)o * e->nlev_d + (s + 1)].d + zskip;
     L.maxbits = e->d_scalars + 1 + (size_t)o * e->nlev_d;
     L.K = K;
     k_extrema_mark<<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
@@ -452,7 +521,8 @@ int s3d_k_extrema_octave(s3d_engine *e, int o, float, double peak_thresh)
     k_extrema_scan<<<1, 1024, 0, e->stream>>>(e->d_blockcnt, nblocks, K, e->d_counter);
     S3D_LAUNCH_CHECK(e);
     k_extrema_emit<<<nblocks, EXT_BLOCK, 0, e->stream>>>(e->d_mask, e->d_blockcnt, nblocks, words,
-                                                        K, o, nx, ny, nz, e->d_cand, e->cand_cap);
+                                                        K, o, nx, ny, nz, zbase, e->d_cand,
+                                                        e->cand_cap);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

@@ -512,7 +512,12 @@ int set_corner_thresh_SIFT3D(SIFT3D *const sift3d, const double corner_thresh)
  * octave 0 (blur outputs copy the source's units, imutil.c:3478) while octaves
  * >= 1 keep the units of the last resize (im_downsample_2x does not touch them,
  * imutil.c:1742-1768). */
-static int push_geometry(SIFT3D *s, Slot *sl)
+static int push_geometry_ex(SIFT3D *s, Slot *sl, const int *zsplit, s3d_comm *comm);
+static int push_geometry(SIFT3D *s, Slot *sl) { return push_geometry_ex(s, sl, NULL, NULL); }
+
+/* zsplit/comm != NULL: Z-slab tiling (the geometry pushed is the GLOBAL one; the engine
+ * derives this rank's share, see include/sift3d_cuda.h) */
+static int push_geometry_ex(SIFT3D *s, Slot *sl, const int *zsplit, s3d_comm *comm)
 {
     const Pyramid *g = &s->gpyr, *d = &s->dog;
     const int ng = g->num_levels * g->num_octaves, nd = d->num_levels * d->num_octaves;
@@ -544,14 +549,17 @@ static int push_geometry(SIFT3D *s, Slot *sl)
         g->levels[i].ux = gg[i].ux, g->levels[i].uy = gg[i].uy, g->levels[i].uz = gg[i].uz;
     for (i = 0; i < nd; i++)
         d->levels[i].ux = dd[i].ux, d->levels[i].uy = dd[i].uy, d->levels[i].uz = dd[i].uz;
-    rc = s3d_pyramid_resize(sl->eng, g->num_octaves, g->num_kp_levels, gg, dd);
     first.taps = s->gss.first_gauss.f.kernel;
     first.width = s->gss.first_gauss.f.width;
     for (i = 0; i < s->gss.num_filters; i++) {
         oct[i].taps = s->gss.gauss_octave[i].f.kernel;
         oct[i].width = s->gss.gauss_octave[i].f.width;
     }
-    if (!rc) rc = s3d_pyramid_filters(sl->eng, &first, oct, s->gss.num_filters);
+    rc = s3d_pyramid_filters(sl->eng, &first, oct, s->gss.num_filters);
+    if (!rc)
+        rc = comm ? s3d_slab_pyramid_resize(sl->eng, comm, g->num_octaves, g->num_kp_levels, gg,
+                                            dd, zsplit)
+                  : s3d_pyramid_resize(sl->eng, g->num_octaves, g->num_kp_levels, gg, dd);
     free(gg);
     free(oct);
     return rc ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
@@ -791,8 +799,57 @@ static int set_image(SIFT3D *const s, const Image *const im)
     return push_geometry(s, sl);
 }
 
+/* Z-slab tiling: `im` holds this rank's planes [zsplit[rank], zsplit[rank+1]) of a volume of
+ * zsplit[nranks] planes; sift3d->im takes the GLOBAL dims so that the pyramid geometry
+ * (resize_SIFT3D, sift.c:938-986) and verify_keys (sift.c:2050) see the whole volume. */
+static int set_image_slab(SIFT3D *const s, const Image *const im, const int *zsplit, s3d_comm *comm)
+{
+    Slot *sl = slot_get(s);
+    s3d_engine *e = engine_of(s);
+    const int rank = s3d_comm_rank(comm), nr = s3d_comm_size(comm);
+    const int NZ = zsplit[nr];
+    if (!e || !sl) return SIFT3D_FAILURE;
+    if (im->nz != zsplit[rank + 1] - zsplit[rank] || (im->nz > 0 && im->data == NULL) ||
+        im->nx < 1 || im->ny < 1 || NZ < 1) {
+        ERR("SIFT3D_detect_keypoints_slab: slab of %d planes does not match the split [%d, %d) \n",
+            im->nz, zsplit[rank], zsplit[rank + 1]);
+        return SIFT3D_FAILURE;
+    }
+    s->im.nx = im->nx, s->im.ny = im->ny, s->im.nz = NZ;
+    s->im.ux = im->ux, s->im.uy = im->uy, s->im.uz = im->uz;
+    s->im.nc = im->nc;
+    image_default_stride(&s->im);
+    s->im.size = (size_t)im->nx * im->ny * NZ * im->nc;
+    sl->have_image = 1;
+    if (resize_all(s, s->gpyr.num_kp_levels)) return SIFT3D_FAILURE;
+    if (push_geometry_ex(s, sl, zsplit, comm)) return SIFT3D_FAILURE;
+    return s3d_slab_image_upload(e, im->data, im->xs, im->ys, im->zs) ? SIFT3D_FAILURE
+                                                                      : SIFT3D_SUCCESS;
+}
+
+static int detect_common(SIFT3D *const sift3d, const Image *const im, Keypoint_store *const kp,
+                         const int *zsplit, s3d_comm *comm);
+
 int SIFT3D_detect_keypoints(SIFT3D *const sift3d, const Image *const im, Keypoint_store *const kp)
 { /* sift.c:1609-1641 */
+    return detect_common(sift3d, im, kp, NULL, NULL);
+}
+
+/* Extension (no reference counterpart): SIFT3D_detect_keypoints on one Z-slab of a volume
+ * that is tiled over the ranks of `comm` (s3d_comm_create_nccl / _local).  `kp` receives this
+ * rank's keypoints -- global coordinates, reference scan order -- so that concatenating the
+ * ranks' lists per (octave, level) reproduces the single-volume result.  A following
+ * SIFT3D_extract_descriptors works on them unchanged. */
+int SIFT3D_detect_keypoints_slab(SIFT3D *const sift3d, const Image *const im, const int *zsplit,
+                                 void *comm, Keypoint_store *const kp)
+{
+    if (!comm || !zsplit) return SIFT3D_FAILURE;
+    return detect_common(sift3d, im, kp, zsplit, (s3d_comm *)comm);
+}
+
+static int detect_common(SIFT3D *const sift3d, const Image *const im, Keypoint_store *const kp,
+                         const int *zsplit, s3d_comm *comm)
+{
     Slot *sl;
     s3d_engine *e;
     s3d_keypoint *tmp = NULL;
@@ -802,7 +859,8 @@ int SIFT3D_detect_keypoints(SIFT3D *const sift3d, const Image *const im, Keypoin
             "single-channel images are supported \n", im->nc);
         return SIFT3D_FAILURE;
     }
-    if (set_image(sift3d, im)) return SIFT3D_FAILURE;
+    if (comm ? set_image_slab(sift3d, im, zsplit, comm) : set_image(sift3d, im))
+        return SIFT3D_FAILURE;
     sl = slot_get(sift3d);
     e = sl->eng;
     if (sift3d->dog.num_levels < 3) { /* detect_extrema, sift.c:1089-1093 */
