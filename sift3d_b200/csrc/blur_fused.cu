@@ -443,20 +443,22 @@ bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps,
 }
 
 int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
-                          const TapSet &taps, int zb, int ze);
+                          const TapSet &taps, int zb, int ze, int gz0, int nz_glob);
 
 int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
                    const TapSet &taps, const float uf[3])
 {
     (void)uf;
-    return s3d_blur_fused_zrange(e, src, dst, nx, ny, nz, taps, 0, nz);
+    return s3d_blur_fused_zrange(e, src, dst, nx, ny, nz, taps, 0, nz, 0, nz);
 }
 
 // Output planes [zb, ze) only (Z-slab tiling: the planes outside are halo, filled by the
-// neighbours).  The z mirror rules key on plane 0 / nz-1 of the buffer, which a tiled caller
-// arranges to be true volume ends or out of the filter's reach.
+// neighbours).  The buffer is the window [gz0, gz0 + nz) of a volume of nz_glob planes; the z
+// mirror rules key on plane 0 / nz-1 of the buffer, which a tiled caller arranges to be true
+// volume ends or out of the filter's reach.  The right-hand mirror weights are the f32
+// roundings of expressions in the GLOBAL plane index, so the table is built from nz_glob.
 int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
-                          const TapSet &taps, int zb, int ze)
+                          const TapSet &taps, int zb, int ze, int gz0, int nz_glob)
 {
     const int hw = taps.width / 2;
     const int nzr = ze - zb;
@@ -547,7 +549,8 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
     P.seg_start = reinterpret_cast<const int *>((const unsigned char *)d_tab + nseg * sizeof(Seg));
     mirror_table(nx, P.mx);
     mirror_table(ny, P.my);
-    mirror_table(nz, P.mz);
+    mirror_table(nz_glob, P.mz);
+    for (int k = 0; k <= MAXHW; k++) P.mz.lo[k] -= gz0;  // global plane -> buffer plane
     P.taps = taps;
     P.c_negzero = -0.0f;
     P.c_one = 1.0f;

@@ -156,10 +156,11 @@ int s3d_k_max_abs(s3d_engine *e, const float *x, size_t n, unsigned *d_bits);
 int s3d_k_scale(s3d_engine *e, const float *src, float *dst, size_t n, const unsigned *d_bits);
 int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz, int nc,
                const TapSet &taps, const float uf[3]);
-// same, output restricted to planes [zb, ze) (src planes within the filter's z reach of that
-// range must be valid; mirrors apply at plane 0 / nz-1 only, i.e. at true volume ends)
+// same, output restricted to planes [zb, ze) of a buffer that is the window
+// [gz0, gz0 + nz) of a volume of nz_glob planes (src planes within the filter's z reach of
+// the range must be valid; the mirror rules apply at the true volume ends only)
 int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
-                      const TapSet &taps, const float uf[3], int zb, int ze);
+                      const TapSet &taps, const float uf[3], int zb, int ze, int gz0, int nz_glob);
 // planes beyond an output plane that a z pass with these taps reads (incl. the lerp partner)
 int s3d_blur_z_reach(const TapSet &taps, float ufz);
 int s3d_k_decimate(s3d_engine *e, const float *src, int sx, int sy, int sz, float *dst, int dx,

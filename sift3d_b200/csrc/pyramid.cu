@@ -90,29 +90,36 @@ __global__ void __launch_bounds__(256) k_scale(const float *__restrict__ src,
 // spacing `uf` (= unit / units[axis], not necessarily dyadic).  This is the
 // reference-semantics path: slow but exact for every input; the fused kernel in
 // blur_fused.cu is the fast path for the common case.
+// `gbase`/`nbuf`: the line may be a window [gbase, gbase + nbuf) of a longer (global) line
+// (Z-slab tiling): coordinates are GLOBAL -- the f32 rounding of c, of the mirrored c and of
+// frac depends on the magnitude of the index -- and only the addressing is shifted.
 __device__ __forceinline__ float samp_acc(float acc, float tap, float c, const float *line,
-                                          size_t st, int dim_end)
+                                          size_t st, int dim_end, int gbase, int nbuf)
 {
     int lo = __float2int_rz(c);
     const float frac = __fsub_rn(c, (float)lo);
     int hi = lo + 1;
     lo = min(max(lo, 0), dim_end);  // reads the reference leaves undefined are clamped
     hi = min(max(hi, 0), dim_end);
+    lo = min(max(lo - gbase, 0), nbuf - 1);
+    hi = min(max(hi - gbase, 0), nbuf - 1);
     const float v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, frac), __ldg(line + (size_t)lo * st)),
                               __fmul_rn(frac, __ldg(line + (size_t)hi * st)));
     return __fadd_rn(acc, __fmul_rn(tap, v));
 }
 
-// For AXIS == 2 the launch may cover only the output planes [zoff, zoff + nz) of a line that
-// is nfull planes long: `src` is the base of the whole buffer, `dst` points at plane zoff.
+// For AXIS == 2 the launch may cover only the output planes [zoff, zoff + nz) of a buffer of
+// nbuf planes which is itself the window [gbase, gbase + nbuf) of a line of nglob planes:
+// `src` is the base of the buffer, `dst` points at its plane zoff.
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src,
                                                    float *__restrict__ dst, int nx, int ny,
                                                    int nz, int nc, const TapSet taps, float uf,
-                                                   int zoff, int nfull)
+                                                   int zoff, int nbuf, int gbase, int nglob)
 {
     const size_t total = (size_t)nx * ny * nz * nc;
-    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nfull);
+    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nglob);
+    if (AXIS != 2) nbuf = n, gbase = 0;
     const size_t st = AXIS == 0 ? (size_t)nc : (AXIS == 1 ? (size_t)nc * nx : (size_t)nc * nx * ny);
     const int hw = taps.width / 2;
     const int dim_end = n - 1;
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src
         r /= nx;
         const int y = (int)(r % ny);
         const int z = (int)(r / ny);
-        const int i = AXIS == 0 ? x : (AXIS == 1 ? y : z + zoff);
+        const int i = AXIS == 0 ? x : (AXIS == 1 ? y : z + zoff + gbase);  // global index
         const float *line = src + (idx - (size_t)(AXIS == 2 ? z : i) * st);
         float acc = 0.0f;
         if (i >= start && i <= end) {
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src
             for (int d = -hw; d <= hw; d++) {
                 const float step = __fmul_rn((float)d, uf);
                 c = __fsub_rn(c, step);
-                acc = samp_acc(acc, taps.t[d + hw], c, line, st, dim_end);
+                acc = samp_acc(acc, taps.t[d + hw], c, line, st, dim_end, gbase, nbuf);
                 c = __fadd_rn(c, step);
             }
         } else {
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src
                     c = -c;
                 else if (__float2int_rz(c) >= dim_end)
                     c = __fsub_rn(__fsub_rn(__fmul_rn(2.0f, (float)dim_end), c), conv_eps);
-                acc = samp_acc(acc, taps.t[d + hw], c, line, st, dim_end);
+                acc = samp_acc(acc, taps.t[d + hw], c, line, st, dim_end, gbase, nbuf);
             }
         }
         dst[idx] = acc;
@@ -417,13 +424,13 @@ int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int 
     if (s3d_ensure_scratch(e, total)) return -1;
     const int grid = grid_for(e, total, 256, 16);
     k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0],
-                                               0, nz);
+                                               0, nz, 0, nz);
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
-                                               taps, uf[1], 0, nz);
+                                               taps, uf[1], 0, nz, 0, nz);
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2],
-                                               0, nz);
+                                               0, nz, 0, nz);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -434,17 +441,18 @@ int s3d_blur_z_reach(const TapSet &taps, float ufz)
 }
 
 int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
-                          const TapSet &taps, int zb, int ze);  // blur_fused.cu
+                          const TapSet &taps, int zb, int ze, int gz0, int nz_glob);  // blur_fused.cu
 
 int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
-                      const TapSet &taps, const float uf[3], int zb, int ze)
+                      const TapSet &taps, const float uf[3], int zb, int ze, int gz0, int nz_glob)
 {
     if (ze <= zb) return 0;
     if (e->blur_mode == 0 && s3d_blur_fused_eligible(nx, ny, nz, 1, taps, uf))
-        return s3d_blur_fused_zrange(e, src, dst, nx, ny, nz, taps, zb, ze);
+        return s3d_blur_fused_zrange(e, src, dst, nx, ny, nz, taps, zb, ze, gz0, nz_glob);
     // x and y passes on the planes the z pass will read, then the z pass on [zb, ze).  The
-    // scratch volumes hold planes [p0, p1) only; p0 == 0 / p1 == nz exactly when the range
-    // touches a true end of the line, so the mirror rules see the right geometry.
+    // scratch volumes hold planes [p0, p1) only; the z pass computes its sample coordinates
+    // with GLOBAL plane indices (buffer plane 0 = global plane gz0) so that every f32
+    // rounding -- incl. the mirror at the true end of the volume -- is the whole-volume one.
     const int h = s3d_blur_z_reach(taps, uf[2]);
     const int p0 = std::max(0, zb - h), p1 = std::min(nz, ze + h);
     const size_t plane = (size_t)nx * ny;
@@ -452,13 +460,14 @@ int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int n
     if (s3d_ensure_scratch(e, sub)) return -1;
     const int grid = grid_for(e, sub, 256, 16);
     k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src + plane * p0, e->scratch[0], nx, ny, p1 - p0, 1,
-                                               taps, uf[0], 0, p1 - p0);
+                                               taps, uf[0], 0, 0, 0, 0);
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, p1 - p0, 1,
-                                               taps, uf[1], 0, p1 - p0);
+                                               taps, uf[1], 0, 0, 0, 0);
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<2><<<grid_for(e, plane * (size_t)(ze - zb), 256, 16), 256, 0, e->stream>>>(
-        e->scratch[1], dst + plane * zb, nx, ny, ze - zb, 1, taps, uf[2], zb - p0, p1 - p0);
+        e->scratch[1], dst + plane * zb, nx, ny, ze - zb, 1, taps, uf[2], zb - p0, p1 - p0,
+        gz0 + p0, nz_glob);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

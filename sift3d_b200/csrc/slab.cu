@@ -347,7 +347,7 @@ int s3d_slab_build_pyramid(s3d_engine *e)
     level_uf(G0);
     if (slab_exchange(e, e->im, 0, s3d_blur_z_reach(e->first_taps, uf[2]))) return -1;
     if (s3d_k_blur_zrange(e, e->im, e->g[0].d, G0.nx, G0.ny, S0.hi - S0.lo, e->first_taps, uf,
-                          S0.own0 - S0.lo, S0.own1 - S0.lo))
+                          S0.own0 - S0.lo, S0.own1 - S0.lo, S0.lo, S0.NZ))
         return -1;
     for (int o = 0; o < e->noct; o++) {
         const SlabOct &S = e->slab[o];
@@ -359,7 +359,7 @@ int s3d_slab_build_pyramid(s3d_engine *e)
             if (s == nlg - 1) break;
             LevelDev &dst = e->g[(size_t)o * nlg + s + 1];
             if (s3d_k_blur_zrange(e, cur.d, dst.d, G.nx, G.ny, S.hi - S.lo, e->oct_taps[s], uf,
-                                  S.own0 - S.lo, S.own1 - S.lo))
+                                  S.own0 - S.lo, S.own1 - S.lo, S.lo, S.NZ))
                 return -1;
         }
         if (o != e->noct - 1) {  // im_downsample_2x of level max(s_end-2, first) (sift.c:1029-1041)
