@@ -45,36 +45,8 @@ HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback if MEASURED_PEAKS.json i
 
 
 def blob_volume_torch(n, seed, device):
-    """SURVEY.md Appendix C generator evaluated with torch (fast at 512^3): signed Gaussian
-    blobs at sigma 2,3,4,6,8 + 0.01*U[0,1) noise, shifted to min 0.  float32 [z][y][x]."""
-    import torch
-    import torch.nn.functional as F
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    vol = torch.zeros((n, n, n), dtype=torch.float32, device=device)
-    for sig in (2, 3, 4, 6, 8):
-        k = max(1, int(n ** 3 / (64 * sig ** 3)))
-        idx = torch.randint(0, n, (k, 3), generator=g)
-        amp = (torch.rand(k, generator=g) * 2 - 1).float() * sig ** 3
-        imp = torch.zeros((n, n, n), dtype=torch.float32, device=device)
-        imp.index_put_((idx[:, 0].to(device), idx[:, 1].to(device), idx[:, 2].to(device)),
-                       amp.to(device), accumulate=True)
-        r = int(4 * sig)
-        x = torch.arange(-r, r + 1, dtype=torch.float32, device=device)
-        w = torch.exp(-0.5 * (x / sig) ** 2)
-        w = w / w.sum()
-        t = imp[None, None]
-        for ax in range(3):
-            shape = [1, 1, 1, 1, 1]
-            shape[2 + ax] = 2 * r + 1
-            pad = [0, 0, 0, 0, 0, 0]
-            pad[2 * (2 - ax)] = pad[2 * (2 - ax) + 1] = r
-            t = F.conv3d(F.pad(t, pad, mode="reflect"), w.view(shape))
-        vol += t[0, 0]
-        del imp, t
-    noise = torch.rand((n, n, n), generator=g, dtype=torch.float32)
-    vol += 0.01 * noise.to(device)
-    vol -= vol.min()
-    return vol.contiguous()
+    from sift3d_b200.volumes import blob_volume_torch as gen
+    return gen((n, n, n), seed, device)
 
 
 class ClockSampler:
