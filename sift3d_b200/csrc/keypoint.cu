@@ -597,10 +597,23 @@ __global__ void __launch_bounds__(DESC_THREADS)
 //            far apart, i.e. in different spatial cells) and every lane does the full
 //            per-voxel work: gradient, glibc-exact window weight, rotation, icosahedron bin,
 //            24 histogram updates.
-// The histogram is 64-bit FIXED POINT (2^-32 units, lo/hi words updated with native 32-bit
-// shared atomics and an explicit carry): integer addition is associative, so the descriptor is
-// bit-reproducible from run to run, and same-address conflicts cost no retry loops.
+// The histogram is FIXED POINT: integer addition is associative, so the descriptor is
+// bit-reproducible from run to run (and between a tiled and a whole-volume run), and only
+// native 32-bit shared atomics are needed (f32 / 64-bit shared atomics are CAS loops in SASS).
+// A contribution c * 2^S (S chosen per keypoint so that |c * 2^S| < 2^31) is rounded to an
+// int32 q and added to a lo/hi word pair:
+//   FX_CARRY = 1: lo += q (mod 2^32) with ONE ATOMS whose returned old value gives the carry;
+//     hi += sign(q) + carry, which is almost always zero (no second atomic).  The three updates
+//     of a corner are issued together so their round trips overlap.
+//   FX_CARRY = 0: two fire-and-forget ATOMS, lo += q & 0xffff and hi += q >> 16 (arithmetic
+//     shift, so q == hi * 65536 + lo for negative q too); needs < 32768 contributions per bin,
+//     checked per keypoint from the size of a cell's support.  Fewer instructions but twice the
+//     shared-memory wavefronts, which is what bounds this kernel (ncu: LSU data pipe 83 %).
+// Windows too large for either take the 2^-32 / explicit 64-bit carry path.
 #define DESC2_THREADS 256
+#ifndef FX_CARRY
+#define FX_CARRY 1
+#endif
 #define DESC2_LIST 9216  // entries; split into one segment per warp
 
 __global__ void __launch_bounds__(DESC2_THREADS, 4)
@@ -608,8 +621,12 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
     __shared__ unsigned list[DESC2_LIST];
-    __shared__ unsigned h_lo[S3D_DESC_NUMEL + 32];  // +32: per-lane dummy slots (out-of-grid corners)
-    __shared__ int h_hi[S3D_DESC_NUMEL + 32];
+    // lo and hi words of the fixed-point histogram in ONE array, so that both atomics of an
+    // update share an address register; +48: dummy slots for out-of-grid corners (lane + vertex)
+    constexpr int HSTRIDE = S3D_DESC_NUMEL + 48;
+    __shared__ int h_fx[2 * HSTRIDE];
+    unsigned *h_lo = reinterpret_cast<unsigned *>(h_fx);
+    int *h_hi = h_fx + HSTRIDE;
     float *hist = reinterpret_cast<float *>(list);  // the list is dead when hist is written
     __shared__ unsigned long long s_tab[32];
     __shared__ double s_red[DESC2_THREADS / 32];
@@ -645,9 +662,21 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
 #pragma unroll
         for (int j = 0; j < 3; j++) Rt[3 * i + j] = kp.R[3 * j + i];
 
-    for (int i = tid; i < S3D_DESC_NUMEL + 32; i += DESC2_THREADS) {
-        h_lo[i] = 0u;
-        h_hi[i] = 0;
+    for (int i = tid; i < 2 * HSTRIDE; i += DESC2_THREADS) h_fx[i] = 0;
+    // Fixed-point mode of this keypoint (block-uniform).  |level| <= 1 after im_scale
+    // (imutil.c:1977; the blurs are convex combinations), so a gradient component is at most
+    // 1/unit and |contribution| <= mag_max = sqrt(iux^2 + iuy^2 + iuz^2): S = the largest
+    // power of two with mag_max * 2^S < 2^31.  A bin's support is a cube of side
+    // 2 * hist_width: it must hold < 32768 voxels for the 16-bit halves not to overflow.
+    float fx_scale;
+    bool split;
+    {
+        const float mag_max = sqrtf(iux * iux + iuy * iuy + iuz * iuz) * 1.01f;
+        int ex;
+        frexpf(mag_max, &ex);  // mag_max < 2^ex
+        fx_scale = ldexpf(1.0f, 31 - ex);
+        const float support = 8.0f * hist_width * hist_width * hist_width * iux * iuy * iuz;
+        split = ex <= 31 && ex >= -60 && (FX_CARRY || support * 1.25f + 512.0f < 32768.0f);
     }
     if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
     load_faces(s_face, s_lut, M);
@@ -751,25 +780,78 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                 ib[a] = (int)vb[a];
             }
             const int i0 = s_face[bin].idx[0], i1 = s_face[bin].idx[1], i2 = s_face[bin].idx[2];
+            // mag * 2^S: scaling by a power of two commutes with every rounding below, so
+            // fm(fm(mag_s, wgt), bary) == fm(fm(mag, wgt), bary) * 2^S (sift.c:1763-1765)
+            const float mag_s = fm(mag, split ? fx_scale : 4294967296.0f);
+            const bool small = mag_s < 2147480000.0f;  // |contribution| < 2^31 (bary <= 1 + eps)
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 const int cx = ib[0] + (c >> 2), cy = ib[1] + ((c >> 1) & 1), cz = ib[2] + (c & 1);
-                // corners outside the 4x4x4 grid add nothing: they are steered to a per-lane
-                // dummy slot so that the scatter stays branch-free
+                // corners outside the 4x4x4 grid add nothing: they are steered to per-lane
+                // dummy slots so that the scatter stays branch-free
                 const bool in = cx < 4 && cy < 4 && cz < 4;
-                const int cell = 12 * (cx + 4 * cy + 16 * cz);
+                int *cell = h_fx + (in ? 12 * (cx + 4 * cy + 16 * cz) : S3D_DESC_NUMEL + lane);
                 const float wgt = fm(fm((c >> 2) ? dv[0] : fs(1.0f, dv[0]),
                                         ((c >> 1) & 1) ? dv[1] : fs(1.0f, dv[1])),
                                      (c & 1) ? dv[2] : fs(1.0f, dv[2]));
-                const float mw = fm(mag, wgt);  // (mag * weight) * bary_j, sift.c:1763-1765
+                const float mw = fm(mag_s, wgt);
+                if (split && small) {
+                    if (FX_CARRY) {
+                        int q[3], qh[3];
+                        unsigned old[3];
+                        int *bp[3];
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const int b = in ? cell + (j == 0 ? i0 : (j == 1 ? i1 : i2)) : S3D_DESC_NUMEL + lane;
-                    const long long q = __float2ll_rn(fm(fm(mw, bary[j]), 4294967296.0f));
-                    const unsigned ql = (unsigned)q;
-                    const unsigned old = atomicAdd(&h_lo[b], ql);
-                    const int qh = (int)(q >> 32) + ((old + ql) < old ? 1 : 0);
-                    if (qh) atomicAdd(&h_hi[b], qh);  // carry / sign word: rare
+                        for (int j = 0; j < 3; j++) {
+                            bp[j] = cell + (j == 0 ? i0 : (j == 1 ? i1 : i2));
+                            q[j] = __float2int_rn(fm(mw, bary[j]));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 3; j++)
+                            old[j] = atomicAdd(reinterpret_cast<unsigned *>(bp[j]), (unsigned)q[j]);
+#pragma unroll
+                        for (int j = 0; j < 3; j++)
+                            qh[j] = (q[j] >> 31) + ((old[j] + (unsigned)q[j]) < old[j] ? 1 : 0);
+                        if (qh[0] | qh[1] | qh[2]) {
+#pragma unroll
+                            for (int j = 0; j < 3; j++)
+                                if (qh[j]) atomicAdd(bp[j] + HSTRIDE, qh[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            int *b = cell + (j == 0 ? i0 : (j == 1 ? i1 : i2));
+                            const int q = __float2int_rn(fm(mw, bary[j]));
+                            atomicAdd(b, q & 0xffff);
+                            atomicAdd(b + HSTRIDE, q >> 16);
+                        }
+                    }
+                } else if (split) {  // a contribution of 2^31 units or more (never for |image| <= 1)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        int *b = cell + (j == 0 ? i0 : (j == 1 ? i1 : i2));
+                        const float cj = rintf(fm(mw, bary[j]));  // integer-valued
+                        if (FX_CARRY) {
+                            const long long q = __float2ll_rn(cj);
+                            const unsigned ql = (unsigned)q;
+                            const unsigned old = atomicAdd(reinterpret_cast<unsigned *>(b), ql);
+                            const int qh = (int)(q >> 32) + ((old + ql) < old ? 1 : 0);
+                            if (qh) atomicAdd(b + HSTRIDE, qh);
+                        } else {
+                            const float hi = floorf(cj * (1.0f / 65536.0f));  // exact
+                            atomicAdd(b, __float2int_rn(cj - hi * 65536.0f));
+                            atomicAdd(b + HSTRIDE, __float2int_rn(hi));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        int *b = cell + (j == 0 ? i0 : (j == 1 ? i1 : i2));
+                        const long long q = __float2ll_rn(fm(mw, bary[j]));
+                        const unsigned ql = (unsigned)q;
+                        const unsigned old = atomicAdd(reinterpret_cast<unsigned *>(b), ql);
+                        const int qh = (int)(q >> 32) + ((old + ql) < old ? 1 : 0);
+                        if (qh) atomicAdd(b + HSTRIDE, qh);  // carry / sign word: rare
+                    }
                 }
             }
         }
@@ -779,8 +861,13 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
 
     // fixed point -> f32
     for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) {
-        const long long v = ((long long)h_hi[i] << 32) | (long long)h_lo[i];
-        hist[i] = (float)((double)v * (1.0 / 4294967296.0));
+        if (split && !FX_CARRY) {
+            const long long v = (long long)h_hi[i] * 65536ll + (long long)(int)h_lo[i];
+            hist[i] = (float)((double)v * (1.0 / (double)fx_scale));
+        } else {
+            const long long v = ((long long)h_hi[i] << 32) + (long long)h_lo[i];
+            hist[i] = (float)((double)v * (1.0 / (split ? (double)fx_scale : 4294967296.0)));
+        }
     }
     __syncthreads();
 
