@@ -179,6 +179,28 @@ int s3d_slab_image_from_device(s3d_engine *e, const float *dev);
 /* info = {own0, own1, lo, hi, NZ, halo} of octave o: owned planes, planes held, global count. */
 int s3d_slab_info(const s3d_engine *e, int o, int info[6]);
 
+/* ---- descriptor matching -------------------------------------------
+ * SIFT3D_nn_match / match_desc (sift.c:2840-2969): nearest + second-nearest by f64 SSD over
+ * the 768 histogram values (accumulated in the reference's order, bit-identical), ratio test
+ * ssd_best / ssd_nearest > nn_thresh^2, forward-backward consistency.  d1/d2: records of
+ * S3D_DESC_STRIDE bytes; matches[i] = index into d2 or -1. */
+int s3d_nn_match(s3d_engine *e, const void *host_d1, int n1, const void *host_d2, int n2,
+                 float nn_thresh, int *host_matches);
+int s3d_nn_match_device(s3d_engine *e, const void *dev_d1, int n1, const void *dev_d2, int n2,
+                        float nn_thresh, int *dev_matches);
+
+/* ---- resampling ------------------------------------------------------
+ * im_inv_transform (imutil.c:2040-2081) for an Affine tform (apply_Affine_xyz,
+ * imutil.c:2651): dst[x,y,z,c] = resample(src, A * [x y z 1]^T), A row-major 3x4 in f64;
+ * interp 0 = LINEAR (resample_linear, imutil.c:2085: trilinear in f64, zero outside
+ * [0, n-1]; bit-identical to the CPU), 1 = LANCZOS2 (resample_lanczos2, imutil.c:2127).
+ * Volumes are contiguous, channel-interleaved (im_default_stride, imutil.c:1453). */
+int s3d_resample_affine(s3d_engine *e, const float *host_src, int nx, int ny, int nz, int nc,
+                        const double A[12], int interp, float *host_dst, int dnx, int dny, int dnz);
+int s3d_resample_affine_device(s3d_engine *e, const float *dev_src, int nx, int ny, int nz, int nc,
+                               const double A[12], int interp, float *dev_dst, int dnx, int dny,
+                               int dnz);
+
 /* ---- kernel-level entry (tests / bench roofline): device pointers ------------ */
 /* apply_Sep_FIR_filter (imutil.c:3459): x, y, z passes, nc interleaved channels. */
 int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx, int ny, int nz,

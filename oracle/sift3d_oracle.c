@@ -914,3 +914,118 @@ postproc:
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ resampling (8f N3)
+ * im_inv_transform (imutil.c:2040-2081) for an Affine (apply_Affine_xyz, imutil.c:2651-2672)
+ * with resample_linear (imutil.c:2085-2124) or resample_lanczos2 (imutil.c:2127-2178).
+ * A: row-major 3x4.  Volumes contiguous, channel-interleaved. */
+static double orc_lanczos(double x, double a)
+{ /* imutil.c:2181-2185 */
+    const double pi_x = M_PI * x;
+    return a * sin(pi_x) * sin(pi_x / a) / (pi_x * pi_x);
+}
+
+int orc_resample_affine(const float *src, int nx, int ny, int nz, int nc, const double A[12],
+                        int interp, float *dst, int dnx, int dny, int dnz)
+{
+    const size_t sxs = nc, sys = (size_t)nc * nx, szs = (size_t)nc * nx * ny;
+    int zi;
+    if (interp != 0 && interp != 1) return -1;
+#pragma omp parallel for schedule(static)
+    for (zi = 0; zi < dnz; zi++) {
+        int xi, yi, c;
+        for (yi = 0; yi < dny; yi++)
+            for (xi = 0; xi < dnx; xi++) {
+                const double xd = xi, yd = yi, zd = zi;
+                const double x = A[0] * xd + A[1] * yd + A[2] * zd + A[3];
+                const double y = A[4] * xd + A[5] * yd + A[6] * zd + A[7];
+                const double z = A[8] * xd + A[9] * yd + A[10] * zd + A[11];
+                float *out = dst + (size_t)nc * (xi + (size_t)dnx * (yi + (size_t)dny * zi));
+                if (x < 0 || x > nx - 1 || y < 0 || y > ny - 1 || z < 0 || z > nz - 1) {
+                    for (c = 0; c < nc; c++) out[c] = 0.0f;
+                    continue;
+                }
+                for (c = 0; c < nc; c++) {
+                    const float *p = src + c;
+                    if (interp == 0) {
+                        const int fx = (int)floor(x), fy = (int)floor(y), fz = (int)floor(z);
+                        const int cx = (int)ceil(x), cy = (int)ceil(y), cz = (int)ceil(z);
+                        const double dist_x = x - fx, dist_y = y - fy, dist_z = z - fz;
+                        const double c0 = p[fx * sxs + fy * sys + fz * szs];
+                        const double c1 = p[fx * sxs + cy * sys + fz * szs];
+                        const double c2 = p[cx * sxs + fy * sys + fz * szs];
+                        const double c3 = p[cx * sxs + cy * sys + fz * szs];
+                        const double c4 = p[fx * sxs + fy * sys + cz * szs];
+                        const double c5 = p[fx * sxs + cy * sys + cz * szs];
+                        const double c6 = p[cx * sxs + fy * sys + cz * szs];
+                        const double c7 = p[cx * sxs + cy * sys + cz * szs];
+                        out[c] = (float)(c0 * (1.0 - dist_x) * (1.0 - dist_y) * (1.0 - dist_z) +
+                                         c1 * (1.0 - dist_x) * dist_y * (1.0 - dist_z) +
+                                         c2 * dist_x * (1.0 - dist_y) * (1.0 - dist_z) +
+                                         c3 * dist_x * dist_y * (1.0 - dist_z) +
+                                         c4 * (1.0 - dist_x) * (1.0 - dist_y) * dist_z +
+                                         c5 * (1.0 - dist_x) * dist_y * dist_z +
+                                         c6 * dist_x * (1.0 - dist_y) * dist_z +
+                                         c7 * dist_x * dist_y * dist_z);
+                    } else {
+                        const double a = 2;
+                        const int x0 = (int)ORC_MAX(floor(x) - a, 0.0), x1 = (int)ORC_MIN(floor(x) + a, (double)(nx - 1));
+                        const int y0 = (int)ORC_MAX(floor(y) - a, 0.0), y1 = (int)ORC_MIN(floor(y) + a, (double)(ny - 1));
+                        const int z0 = (int)ORC_MAX(floor(z) - a, 0.0), z1 = (int)ORC_MIN(floor(z) + a, (double)(nz - 1));
+                        double val = 0.0;
+                        int xs, ys, zs;
+                        for (zs = z0; zs <= z1; zs++)
+                            for (ys = y0; ys <= y1; ys++)
+                                for (xs = x0; xs <= x1; xs++) {
+                                    const double xw = fabs((double)xs - x) + DBL_EPSILON;
+                                    const double yw = fabs((double)ys - y) + DBL_EPSILON;
+                                    const double zw = fabs((double)zs - z) + DBL_EPSILON;
+                                    const double k = orc_lanczos(xw, a) * orc_lanczos(yw, a) * orc_lanczos(zw, a);
+                                    val += k * p[xs * sxs + ys * sys + zs * szs];
+                                }
+                        out[c] = (float)val;
+                    }
+                }
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ matching (8f N1)
+ * SIFT3D_nn_match / match_desc (sift.c:2840-2969).  desc: n x 768 floats, row-major. */
+static int orc_match_desc(const float *d, const float *store, int n, float nn_thresh)
+{
+    double ssd_best = DBL_MAX, ssd_nearest = DBL_MAX;
+    int best = -1, i, j;
+    for (i = 0; i < n; i++) {
+        const float *d2 = store + (size_t)768 * i;
+        double ssd = 0.0;
+        for (j = 0; j < 768; j++) {
+            const double diff = (double)d[j] - (double)d2[j];
+            ssd += diff * diff;
+            if (j % 12 == 11 && ssd > ssd_nearest) break; /* early exit per histogram */
+        }
+        if (ssd < ssd_best) {
+            best = i;
+            ssd_nearest = ssd_best;
+            ssd_best = ssd;
+        } else {
+            ssd_nearest = ORC_MIN(ssd_nearest, ssd);
+        }
+    }
+    if (ssd_best / ssd_nearest > nn_thresh * nn_thresh) return -1;
+    return best;
+}
+
+int orc_nn_match(const float *d1, int n1, const float *d2, int n2, float nn_thresh, int *matches)
+{
+    int i;
+    if (n1 < 1) return -1;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (i = 0; i < n1; i++) {
+        int m = orc_match_desc(d1 + (size_t)768 * i, d2, n2, nn_thresh);
+        if (m >= 0 && orc_match_desc(d2 + (size_t)768 * m, d1, n1, nn_thresh) != i) m = -1;
+        matches[i] = m;
+    }
+    return 0;
+}

@@ -79,6 +79,12 @@ int orc_eig3(const double A[9], double Q[9], double L[3]); /* stand-in for dsyev
 /* icosahedron table exactly as init_geometry builds it (sift.c:215-326):
  * v: 20 faces x 3 vertices x 3 coords, idx: 20 x 3 */
 void orc_mesh(float *v, int *idx);
+/* im_inv_transform for an Affine given as row-major 3x4 (imutil.c:2040-2081, :2651-2672);
+ * interp 0 = resample_linear (imutil.c:2085), 1 = resample_lanczos2 (imutil.c:2127) */
+int orc_resample_affine(const float *src, int nx, int ny, int nz, int nc, const double A[12],
+                        int interp, float *dst, int dnx, int dny, int dnz);
+/* SIFT3D_nn_match (sift.c:2840-2969); d1, d2: n x 768 floats */
+int orc_nn_match(const float *d1, int n1, const float *d2, int n2, float nn_thresh, int *matches);
 
 #ifdef __cplusplus
 }

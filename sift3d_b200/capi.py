@@ -360,6 +360,53 @@ class Sift3D:
         self.close()
 
 
+def resample_affine(lib: Sift3DLib, vol: np.ndarray, A, out_shape=None, interp: int = 0,
+                    units=(1.0, 1.0, 1.0)) -> np.ndarray:
+    """`im_inv_transform` (imutil.c:2040) for an affine 3x4 matrix through
+    `sift3d_b200_im_inv_transform_affine`; out_shape None = same dims as the input (resize)."""
+    vol = np.ascontiguousarray(vol, np.float32)
+    nc = vol.shape[3] if vol.ndim == 4 else 1
+    src = make_image(vol, units, nc)
+    dst = empty_image()
+    A = np.ascontiguousarray(A, np.float64).reshape(12)
+    f = lib.lib.sift3d_b200_im_inv_transform_affine
+    f.argtypes = [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.POINTER(Image)]
+    f.restype = C.c_int
+    keep = None
+    if out_shape is not None:
+        dnz, dny, dnx = out_shape
+        keep = np.zeros((dnz, dny, dnx, nc), np.float32)
+        dst = make_image(keep if nc > 1 else keep[..., 0].copy(), units, nc)
+        keep = np.ctypeslib.as_array(dst.data, shape=(dnz * dny * dnx * nc,))
+    rc = f(A.ctypes.data, C.byref(src), interp, 1 if out_shape is None else 0, C.byref(dst))
+    if rc != 0:
+        raise RuntimeError(f"sift3d_b200_im_inv_transform_affine returned {rc}")
+    n = dst.nx * dst.ny * dst.nz * dst.nc
+    arr = np.ctypeslib.as_array(dst.data, shape=(n,)).reshape(
+        (dst.nz, dst.ny, dst.nx) + ((dst.nc,) if vol.ndim == 4 else ())).copy()
+    if out_shape is None:
+        lib._libc.free(C.cast(dst.data, C.c_void_p))
+    return arr
+
+
+def im_resample(lib: Sift3DLib, vol: np.ndarray, units_in, units_out, interp: int = 0):
+    """`im_resample` (imutil.c:2191) through `sift3d_b200_im_resample`."""
+    vol = np.ascontiguousarray(vol, np.float32)
+    src = make_image(vol, units_in)
+    dst = empty_image()
+    u = np.asarray(units_out, np.float64)
+    f = lib.lib.sift3d_b200_im_resample
+    f.argtypes = [C.POINTER(Image), C.c_void_p, C.c_int, C.POINTER(Image)]
+    f.restype = C.c_int
+    if f(C.byref(src), u.ctypes.data, interp, C.byref(dst)) != 0:
+        raise RuntimeError("sift3d_b200_im_resample failed")
+    n = dst.nx * dst.ny * dst.nz
+    arr = np.ctypeslib.as_array(dst.data, shape=(n,)).reshape(dst.nz, dst.ny, dst.nx).copy()
+    meta = (dst.ux, dst.uy, dst.uz)
+    lib._libc.free(C.cast(dst.data, C.c_void_p))
+    return arr, meta
+
+
 def load_b200() -> Sift3DLib:
     return Sift3DLib(B200_LIB, "b200")
 

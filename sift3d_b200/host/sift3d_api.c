@@ -56,6 +56,7 @@ typedef struct Slot {
 } Slot;
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_util_lock = PTHREAD_MUTEX_INITIALIZER; /* serialises the shared engine */
 static Slot **g_slots = NULL; /* stable Slot addresses; index 0 = "no engine" */
 static int g_nslots = 0;
 
@@ -1241,39 +1242,30 @@ int SIFT3D_matches_to_Mat_rm(SIFT3D_Descriptor_store *d1, SIFT3D_Descriptor_stor
 /* match_desc, sift.c:2892-2969.  The reference's early exit never changes the
  * outcome (a partial sum above ssd_nearest can only grow), so the plain full sum
  * below returns the same index. */
-static int match_one(const SIFT3D_Descriptor *d, const SIFT3D_Descriptor_store *store,
-                     float nn_thresh)
+/* Engine for the entry points that take no SIFT3D object (matching, resampling). */
+static s3d_engine *g_util_engine = NULL;
+
+static s3d_engine *util_engine(void)
 {
-    double best = DBL_MAX, nearest = DBL_MAX;
-    int ibest = -1;
-    size_t i;
-    for (i = 0; i < store->num; i++) {
-        const float *a = &d->hists[0].bins[0], *b = &store->buf[i].hists[0].bins[0];
-        double ssd = 0.0;
-        int j;
-        for (j = 0; j < DESC_NUMEL; j++) {
-            const double diff = (double)a[j] - (double)b[j];
-            ssd += diff * diff;
-            if ((j % HIST_NUMEL) == HIST_NUMEL - 1 && ssd > nearest) break;
-        }
-        if (ssd < best) {
-            ibest = (int)i;
-            nearest = best;
-            best = ssd;
-        } else {
-            nearest = MINV(nearest, ssd);
-        }
+    s3d_engine *e;
+    pthread_mutex_lock(&g_lock);
+    if (!g_util_engine && s3d_engine_create(&g_util_engine, -1)) {
+        ERR("sift3d_b200: cannot create the CUDA engine: %s \n", s3d_last_create_error());
+        g_util_engine = NULL;
     }
-    if (best / nearest > nn_thresh * nn_thresh) return -1;
-    return ibest;
+    e = g_util_engine;
+    pthread_mutex_unlock(&g_lock);
+    return e;
 }
 
 int SIFT3D_nn_match(const SIFT3D_Descriptor_store *const d1,
                     const SIFT3D_Descriptor_store *const d2, const float nn_thresh,
                     int **const matches)
-{ /* sift.c:2840-2888: forward-backward consistent nearest neighbour with ratio test */
+{ /* sift.c:2840-2888: forward-backward consistent nearest neighbour with ratio test; the
+   * exhaustive f64 SSD search (match_desc, sift.c:2893-2969) runs on the device */
     const int num = (int)d1->num;
-    int i;
+    s3d_engine *e;
+    int i, rc;
     if (num < 1) {
         ERR("_SIFT3D_nn_match: invalid number of descriptors in d1: %d \n", num);
         return SIFT3D_FAILURE;
@@ -1282,12 +1274,101 @@ int SIFT3D_nn_match(const SIFT3D_Descriptor_store *const d1,
         ERR("_SIFT3D_nn_match: out of memory! \n");
         return SIFT3D_FAILURE;
     }
-#pragma omp parallel for
-    for (i = 0; i < num; i++) {
-        int m = match_one(d1->buf + i, d2, nn_thresh);
-        if (m >= 0 && match_one(d2->buf + m, d1, nn_thresh) != i) m = -1;
-        (*matches)[i] = m;
+    for (i = 0; i < num; i++) (*matches)[i] = -1;
+    if (d2->num < 1) return SIFT3D_SUCCESS; /* match_desc finds nothing in an empty store */
+    if ((e = util_engine()) == NULL) return SIFT3D_FAILURE; /* no CPU fallback */
+    pthread_mutex_lock(&g_util_lock);
+    rc = s3d_nn_match(e, d1->buf, num, d2->buf, (int)d2->num, nn_thresh, *matches);
+    pthread_mutex_unlock(&g_util_lock);
+    return rc ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
+}
+
+/* ============================================================ resampling
+ * The reference keeps these in libimutil (im_inv_transform imutil.c:2040, im_resample
+ * imutil.c:2191); they are exported under sift3d_b200_* names so that both libraries can be
+ * loaded side by side -- INTEGRATION.md shows the two-line forwarding a maintainer adds. */
+
+static int image_resize_data(Image *im)
+{ /* im_resize, imutil.c:1523-1560: realloc when the element count changes */
+    const size_t size = (size_t)im->nx * im->ny * im->nz * im->nc;
+    if (im->nx < 1 || im->ny < 1 || im->nz < 1 || im->nc < 1) {
+        ERR("im_resize: invalid dimensions %d x %d x %d x %d \n", im->nx, im->ny, im->nz, im->nc);
+        return SIFT3D_FAILURE;
     }
+    if (im->size != size || im->data == NULL) {
+        im->size = size;
+        if ((im->data = (float *)safe_realloc(im->data, size * sizeof(float))) == NULL) {
+            im->size = 0;
+            return SIFT3D_FAILURE;
+        }
+    }
+    return SIFT3D_SUCCESS;
+}
+
+/* im_inv_transform for an affine map given as a row-major 3x4 matrix (the `A` of an Affine,
+ * imtypes.h:374-377): dst voxel (x,y,z) takes the value of src at A*[x y z 1].
+ * interp: 0 = LINEAR, 1 = LANCZOS2 (interp_type, imtypes.h:343-346). */
+int sift3d_b200_im_inv_transform_affine(const double A[12], const Image *const src, const int interp,
+                                        const int resize, Image *const dst)
+{
+    s3d_engine *e;
+    float *tmp = NULL;
+    const float *data = src->data;
+    int rc;
+    if (src->data == NULL) return SIFT3D_FAILURE;
+    if (interp != 0 && interp != 1) {
+        ERR("im_inv_transform: unrecognized interpolation type");
+        return SIFT3D_FAILURE;
+    }
+    if (resize) { /* im_copy_dims, imutil.c:1873-1890 */
+        dst->nx = src->nx, dst->ny = src->ny, dst->nz = src->nz, dst->nc = src->nc;
+        dst->ux = src->ux, dst->uy = src->uy, dst->uz = src->uz;
+        image_default_stride(dst);
+        if (image_resize_data(dst)) return SIFT3D_FAILURE;
+    }
+    if (dst->data == NULL || dst->nc != src->nc) return SIFT3D_FAILURE;
+    if ((e = util_engine()) == NULL) return SIFT3D_FAILURE;
+    if (src->xs != (size_t)src->nc || src->ys != (size_t)src->nc * src->nx ||
+        src->zs != (size_t)src->nc * src->nx * src->ny) { /* custom strides: gather first */
+        int x, y, z, c;
+        if ((tmp = (float *)malloc((size_t)src->nx * src->ny * src->nz * src->nc * sizeof(float))) == NULL)
+            return SIFT3D_FAILURE;
+        for (z = 0; z < src->nz; z++)
+            for (y = 0; y < src->ny; y++)
+                for (x = 0; x < src->nx; x++)
+                    for (c = 0; c < src->nc; c++)
+                        tmp[c + (size_t)src->nc * (x + (size_t)src->nx * (y + (size_t)src->ny * z))] =
+                            src->data[c + x * src->xs + y * src->ys + z * src->zs];
+        data = tmp;
+    }
+    image_default_stride(dst);
+    pthread_mutex_lock(&g_util_lock);
+    rc = s3d_resample_affine(e, data, src->nx, src->ny, src->nz, src->nc, A, interp, dst->data,
+                             dst->nx, dst->ny, dst->nz);
+    pthread_mutex_unlock(&g_util_lock);
+    free(tmp);
+    return rc ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
+}
+
+/* im_resample, imutil.c:2191-2244: resample to new voxel units. */
+int sift3d_b200_im_resample(const Image *const src, const double *const units, const int interp,
+                            Image *const dst)
+{
+    double A[12] = {0}, factors[3];
+    const double su[3] = {src->ux, src->uy, src->uz};
+    const int sd[3] = {src->nx, src->ny, src->nz};
+    int dims[3], i;
+    for (i = 0; i < 3; i++) {
+        factors[i] = su[i] / units[i];
+        A[4 * i + i] = 1.0 / factors[i];
+        dims[i] = (int)ceil((double)sd[i] * factors[i]);
+    }
+    dst->nc = src->nc;
+    dst->nx = dims[0], dst->ny = dims[1], dst->nz = dims[2];
+    image_default_stride(dst);
+    if (image_resize_data(dst)) return SIFT3D_FAILURE;
+    if (sift3d_b200_im_inv_transform_affine(A, src, interp, 0, dst)) return SIFT3D_FAILURE;
+    dst->ux = units[0], dst->uy = units[1], dst->uz = units[2];
     return SIFT3D_SUCCESS;
 }
 

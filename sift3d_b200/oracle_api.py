@@ -59,6 +59,11 @@ class Oracle:
         L.orc_eig3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_mesh.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_mesh.restype = None
+        L.orc_resample_affine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int]
+        L.orc_nn_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float,
+                                   C.c_void_p]
         p = OrcParams(peak_thresh, corner_thresh, sigma_n, sigma0, num_kp_levels)
         self.ctx = L.orc_create(C.byref(p))
 
@@ -138,3 +143,25 @@ class Oracle:
         idx = np.zeros((20, 3), np.int32)
         self.L.orc_mesh(v.ctypes.data, idx.ctypes.data)
         return v, idx
+
+    def resample_affine(self, vol, A, out_shape, interp=0):
+        """im_inv_transform for an affine 3x4 `A`; vol [z][y][x] or [z][y][x][c]."""
+        vol = np.ascontiguousarray(vol, np.float32)
+        nc = vol.shape[3] if vol.ndim == 4 else 1
+        nz, ny, nx = vol.shape[:3]
+        A = np.ascontiguousarray(A, np.float64).reshape(12)
+        dnz, dny, dnx = out_shape
+        out = np.zeros((dnz, dny, dnx) + ((nc,) if vol.ndim == 4 else ()), np.float32)
+        if self.L.orc_resample_affine(vol.ctypes.data, nx, ny, nz, nc, A.ctypes.data, interp,
+                                      out.ctypes.data, dnx, dny, dnz):
+            raise RuntimeError("orc_resample_affine failed")
+        return out
+
+    def nn_match(self, d1, d2, nn_thresh=0.8):
+        d1 = np.ascontiguousarray(d1, np.float32)
+        d2 = np.ascontiguousarray(d2, np.float32)
+        out = np.full(len(d1), -2, np.int32)
+        if self.L.orc_nn_match(d1.ctypes.data, len(d1), d2.ctypes.data, len(d2), nn_thresh,
+                               out.ctypes.data):
+            raise RuntimeError("orc_nn_match failed")
+        return out

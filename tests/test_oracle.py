@@ -144,3 +144,90 @@ def test_mesh_quirk(oracle_cls):
         assert np.allclose(v[i, 0], vert[idx[i, 1]], atol=1e-6)
         assert np.allclose(v[i, 1], vert[idx[i, 0]], atol=1e-6)
         assert np.allclose(v[i, 2], vert[idx[i, 2]], atol=1e-6)
+
+
+# ---------------------------------------------------------------- SURVEY.md 8f rows N1 / N3
+def _ref_imutil():
+    from sift3d_b200 import capi
+    if not capi.REF_IMUTIL.exists():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    import ctypes as C
+    return C.CDLL(str(capi.REF_IMUTIL))
+
+
+def _ref_inv_transform(L, vol, A, out_shape, interp):
+    """The unmodified reference: init_Affine + Affine_set_mat + im_inv_transform."""
+    import ctypes as C
+    from sift3d_b200 import capi
+    vol = np.ascontiguousarray(vol, np.float32)
+    nc = vol.shape[3] if vol.ndim == 4 else 1
+    src = capi.make_image(vol, (1.0, 1.0, 1.0), nc)
+    aff = (C.c_char * 64)()                      # Affine: Tform (16 B) + Mat_rm (32 B)
+    assert L.init_Affine(aff, 3) == 0
+    Am = np.ascontiguousarray(A, np.float64).reshape(3, 4)
+    m = capi.Mat_rm()
+    m.data = Am.ctypes.data
+    m.size = Am.nbytes
+    m.num_cols, m.num_rows, m.static_mem, m.type = 4, 3, 1, 0   # SIFT3D_DOUBLE
+    assert L.Affine_set_mat(C.byref(m), aff) == 0
+    dnz, dny, dnx = out_shape
+    out = np.zeros((dnz, dny, dnx) + ((nc,) if vol.ndim == 4 else ()), np.float32)
+    dst = capi.make_image(out, (1.0, 1.0, 1.0), nc)
+    L.im_inv_transform.argtypes = [C.c_void_p, C.POINTER(capi.Image), C.c_int, C.c_int,
+                                   C.POINTER(capi.Image)]
+    assert L.im_inv_transform(aff, C.byref(src), interp, 0, C.byref(dst)) == 0
+    return out
+
+
+AFFINES = {
+    "identity": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0],
+    "scale": [0.5, 0, 0, 0, 0, 1.0 / 0.7, 0, 0, 0, 0, 1.25, 0],
+    "rot_shift": [0.9553, -0.2955, 0.0, 3.1, 0.2955, 0.9553, 0.05, -2.4, -0.03, 0.02, 1.01, 1.7],
+}
+
+
+@pytest.mark.parametrize("name", list(AFFINES))
+@pytest.mark.parametrize("interp", [0, 1])
+def test_resample_restatement_equals_reference(oracle_cls, name, interp):
+    L = _ref_imutil()
+    rng = np.random.default_rng(3)
+    vol = rng.random((14, 17, 19), dtype=np.float32)
+    out_shape = (16, 15, 23)
+    want = _ref_inv_transform(L, vol, AFFINES[name], out_shape, interp)
+    got = oracle_cls().resample_affine(vol, AFFINES[name], out_shape, interp)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (want != 0).mean() > 0.2
+    if interp == 0:                                   # multi-channel, linear
+        v4 = rng.random((6, 7, 8, 3), dtype=np.float32)
+        want = _ref_inv_transform(L, v4, AFFINES[name], (7, 6, 9), 0)
+        got = oracle_cls().resample_affine(v4, AFFINES[name], (7, 6, 9), 0)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_nn_match_restatement_equals_reference(oracle_cls, ref_lib):
+    import ctypes as C
+    from sift3d_b200 import capi
+    rng = np.random.default_rng(5)
+    a = rng.random((60, 771)).astype(np.float32)
+    b = np.concatenate([a[:30] + 0.02 * rng.random((30, 771)).astype(np.float32), a[:5],
+                        rng.random((25, 771)).astype(np.float32)])
+
+    def store(rows):
+        m = capi.Mat_rm()
+        m.data = rows.ctypes.data
+        m.size = rows.nbytes
+        m.num_cols, m.num_rows, m.static_mem, m.type = 771, len(rows), 1, 1
+        d = capi.SIFT3D_Descriptor_store()
+        ref_lib.lib.init_SIFT3D_Descriptor_store(C.byref(d))
+        ref_lib.lib.Mat_rm_to_SIFT3D_Descriptor_store.argtypes = [
+            C.POINTER(capi.Mat_rm), C.POINTER(capi.SIFT3D_Descriptor_store)]
+        assert ref_lib.lib.Mat_rm_to_SIFT3D_Descriptor_store(C.byref(m), C.byref(d)) == 0
+        return d
+    for thresh in (0.8, 0.95):
+        d1, d2 = store(a), store(b)
+        m = C.POINTER(C.c_int)()
+        assert ref_lib.lib.SIFT3D_nn_match(C.byref(d1), C.byref(d2), C.c_float(thresh),
+                                           C.byref(m)) == 0
+        want = np.array([m[i] for i in range(len(a))])
+        got = oracle_cls().nn_match(a[:, 3:], b[:, 3:], thresh)
+        assert np.array_equal(got, want) and (want >= 0).sum() >= 20
