@@ -372,20 +372,20 @@ def resample_affine(lib: Sift3DLib, vol: np.ndarray, A, out_shape=None, interp: 
     f = lib.lib.sift3d_b200_im_inv_transform_affine
     f.argtypes = [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.POINTER(Image)]
     f.restype = C.c_int
-    keep = None
+    out = None
     if out_shape is not None:
         dnz, dny, dnx = out_shape
-        keep = np.zeros((dnz, dny, dnx, nc), np.float32)
-        dst = make_image(keep if nc > 1 else keep[..., 0].copy(), units, nc)
-        keep = np.ctypeslib.as_array(dst.data, shape=(dnz * dny * dnx * nc,))
+        out = np.zeros((dnz, dny, dnx) + ((nc,) if vol.ndim == 4 else ()), np.float32)
+        dst = make_image(out, units, nc)        # `out` stays alive until we return it
     rc = f(A.ctypes.data, C.byref(src), interp, 1 if out_shape is None else 0, C.byref(dst))
     if rc != 0:
         raise RuntimeError(f"sift3d_b200_im_inv_transform_affine returned {rc}")
+    if out is not None:
+        return out
     n = dst.nx * dst.ny * dst.nz * dst.nc
     arr = np.ctypeslib.as_array(dst.data, shape=(n,)).reshape(
         (dst.nz, dst.ny, dst.nx) + ((dst.nc,) if vol.ndim == 4 else ())).copy()
-    if out_shape is None:
-        lib._libc.free(C.cast(dst.data, C.c_void_p))
+    lib._libc.free(C.cast(dst.data, C.c_void_p))
     return arr
 
 
