@@ -39,4 +39,19 @@ gcc $CF $DEFS -I"$R/imutil" -shared "$R/imutil/imutil.c" "$R/imutil/nifti.c" \
     $LAPACK_LINK -lz -lm -lstdc++
 gcc $CF $DEFS -I"$R/imutil" -I"$R/sift3d" -shared "$R/sift3d/sift.c" \
     -o "$OUT/libsift3D_ref.so" -L"$OUT" -limutil_ref -lm -Wl,-rpath,'$ORIGIN'
+# The reference's UNMODIFIED command-line programs, for the end-to-end drop-in test
+# (tests/test_gpu_cli.py, BASELINE.json configs[0]): *_stock resolves libsift3D.so at run time
+# (the test points LD_LIBRARY_PATH at sift3d_b200/lib), *_cpu is bound to the reference build.
+ln -sf libsift3D_ref.so "$OUT/libsift3D.so.cpu"
+for prog in kpSift3D denseSift3D; do
+  gcc -O1 -w $DEFS -I"$R/imutil" -I"$R/sift3d" "$R/cli/$prog.c" -o "$OUT/${prog}_stock" \
+      -L"$HERE/../sift3d_b200/lib" -lsift3D -L"$OUT" -limutil_ref -lm \
+      -Wl,-rpath,'$ORIGIN' -Wl,--allow-shlib-undefined 2>/dev/null || \
+      echo "build_ref: ${prog}_stock not linked (build sift3d_b200/lib first)" >&2
+  gcc -O1 -w $DEFS -I"$R/imutil" -I"$R/sift3d" "$R/cli/$prog.c" -o "$OUT/${prog}_cpu" \
+      -L"$OUT" -lsift3D_ref -limutil_ref -lm -Wl,-rpath,'$ORIGIN' -Wl,--allow-shlib-undefined
+done
+# the reference's example volume (data, not source; _ref/ is git-ignored and travels to the box)
+mkdir -p "$OUT/data"
+cp -f "$R/examples/data/1.nii.gz" "$OUT/data/1.nii.gz"
 echo "build_ref: built $(ls "$OUT")"
