@@ -526,20 +526,28 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
         e->desc_cap = bytes;
     }
     S3D_CUDA(e, cudaMemcpyAsync(e->d_kp_in, kp, (size_t)n * sizeof(s3d_keypoint), cudaMemcpyHostToDevice, e->stream));
-    // chunked: the D2H copy of chunk i (on a second stream) overlaps the kernel of chunk i+1, so
-    // the 3104 B/keypoint of results leave the device behind the compute instead of after it
+    // chunked: every chunk's kernel is queued first (an event after each); the D2H copies then
+    // run on a second stream behind their events.  The caller's buffer is malloc memory (the
+    // reference's ownership contract), and a D2H copy into pageable memory blocks
+    // the host until it is done -- so the copies must be issued AFTER all launches, or chunk
+    // i+1's kernel would wait for chunk i's copy.  This way only the last chunk's copy is
+    // exposed; the rest leave the device behind the compute.
     if (!e->copy_stream) S3D_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     const int chunk = 4096;
     const int nchunks = (n + chunk - 1) / chunk;
-    std::vector<cudaEvent_t> done(nchunks);
+    std::vector<cudaEvent_t> done(nchunks, nullptr);
     int rc = 0;
     for (int c = 0; c < nchunks && !rc; c++) {
         const int lo = c * chunk, cnt = std::min(chunk, n - lo);
         rc = s3d_k_descriptors(e, e->d_kp_in + lo, cnt, e->d_desc + (size_t)lo * S3D_DESC_STRIDE);
         if (rc) break;
         if (cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventRecord(done[c], e->stream) != cudaSuccess ||
-            cudaStreamWaitEvent(e->copy_stream, done[c], 0) != cudaSuccess ||
+            cudaEventRecord(done[c], e->stream) != cudaSuccess)
+            rc = s3d_fail(e, "descriptor events", cudaGetLastError(), __FILE__, __LINE__);
+    }
+    for (int c = 0; c < nchunks && !rc; c++) {
+        const int lo = c * chunk, cnt = std::min(chunk, n - lo);
+        if (cudaStreamWaitEvent(e->copy_stream, done[c], 0) != cudaSuccess ||
             cudaMemcpyAsync((unsigned char *)host_desc + (size_t)lo * S3D_DESC_STRIDE,
                             e->d_desc + (size_t)lo * S3D_DESC_STRIDE, (size_t)cnt * S3D_DESC_STRIDE,
                             cudaMemcpyDeviceToHost, e->copy_stream) != cudaSuccess)

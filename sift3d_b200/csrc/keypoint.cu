@@ -589,14 +589,28 @@ __global__ void __launch_bounds__(DESC_THREADS)
     }
 }
 
-// Descriptor, version 2 (the default).  Per keypoint CTA:
-//   phase A  warps scan the rows of the window's bounding box, pruned to the sphere's x
-//            extent, apply the reference's exact sphere / descriptor-cube tests and append the
-//            surviving voxels to a shared list (ballot + one counter atomic per warp);
-//   phase B  the list is consumed with a strided assignment (neighbouring lanes take voxels
-//            far apart, i.e. in different spatial cells) and every lane does the full
-//            per-voxel work: gradient, glibc-exact window weight, rotation, icosahedron bin,
-//            24 histogram updates.
+// native 32-bit shared-memory atomics on a shared-window byte address
+__device__ __forceinline__ unsigned atoms_add(unsigned addr, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void atoms_inc(unsigned addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+// Descriptor, version 2 (the default).  One CTA (8 warps) per keypoint; every warp owns every
+// 8th row of the window's bounding box, 32 rows per chunk:
+//   phase A  (lane = row) the x interval of the row that can pass the reference's sphere /
+//            descriptor-cube tests -- sphere chord intersected with three slabs linear in x --
+//            in approximate arithmetic, widened to whole voxels; a warp scan of the interval
+//            lengths gives every voxel of the chunk an index;
+//   phase B  (lane = a contiguous share of those indices: its consecutive voxels are x
+//            neighbours, the 32 lanes sit in different rows) the full per-voxel work: the EXACT
+//            tests, gradient, glibc-exact window weight, rotation, icosahedron bin, 24 histogram
+//            updates.
 // The histogram is FIXED POINT: integer addition is associative, so the descriptor is
 // bit-reproducible from run to run (and between a tiled and a whole-volume run), and only
 // native 32-bit shared atomics are needed (f32 / 64-bit shared atomics are CAS loops in SASS).
@@ -614,20 +628,20 @@ __global__ void __launch_bounds__(DESC_THREADS)
 #ifndef FX_CARRY
 #define FX_CARRY 1
 #endif
-#define DESC2_LIST 9216  // entries; split into one segment per warp
 
 __global__ void __launch_bounds__(DESC2_THREADS, 4)
     k_descriptor2(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
-    __shared__ unsigned list[DESC2_LIST];
+    __shared__ int4 s_rows[DESC2_THREADS / 32][33];  // per warp: {first index, xa, y, z} of 32 rows
+    __shared__ float hist[S3D_DESC_NUMEL];
     // lo and hi words of the fixed-point histogram in ONE array, so that both atomics of an
     // update share an address register; +48: dummy slots for out-of-grid corners (lane + vertex)
     constexpr int HSTRIDE = S3D_DESC_NUMEL + 48;
     __shared__ int h_fx[2 * HSTRIDE];
     unsigned *h_lo = reinterpret_cast<unsigned *>(h_fx);
     int *h_hi = h_fx + HSTRIDE;
-    float *hist = reinterpret_cast<float *>(list);  // the list is dead when hist is written
+    const unsigned h_addr = (unsigned)__cvta_generic_to_shared(h_fx);
     __shared__ unsigned long long s_tab[32];
     __shared__ double s_red[DESC2_THREADS / 32];
     __shared__ FaceConst s_face[20];
@@ -706,53 +720,92 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
     };
 
     // Every warp works alone until the final reduction: it owns the rows w, w+8, w+16, ... of
-    // the window box (interleaved for balance), compacts the voxels that pass the exact sphere /
-    // cube tests of a chunk of those rows into ITS list segment (phase A, ballot prefix, no
-    // atomics) and immediately consumes the segment (phase B).  Only __syncwarp between the two;
-    // the static split makes the whole computation -- list order included -- deterministic.
+    // the window box (interleaved for balance), 32 rows per chunk.
+    //   phase A (lane = row): the voxels of a row that can pass the reference's sphere and
+    //     descriptor-cube tests form ONE x interval -- the sphere chord intersected with the three
+    //     slabs 0 <= vb[a] < 4, each linear in x -- computed here in approximate arithmetic and
+    //     widened to whole voxels, so no per-voxel work is spent on selection;
+    //   phase B (lane = a contiguous share of the chunk's voxels, so that its consecutive voxels
+    //     are x neighbours while the 32 lanes sit in different rows): the full per-voxel work,
+    //     starting with the EXACT tests in the reference's f32 operation order, which reject the
+    //     few voxels the widening let through.
+    // Only __syncwarp between the phases; the static split makes the whole computation
+    // deterministic (and the fixed-point histogram makes it order-independent anyway).
     constexpr int NWARP = DESC2_THREADS / 32;
-    constexpr int SEGCAP = DESC2_LIST / NWARP;
-    const int rows_per_chunk = max(SEGCAP / bx_safe, 1);
     (void)rows_per_batch;
-    unsigned *seg = list + warp * SEGCAP;
+    (void)bx_safe;
+    int4 *rows = s_rows[warp];
     const int my_rows = bx > 0 && nrows > warp ? (nrows - warp + NWARP - 1) / NWARP : 0;
-    for (int rc = 0; rc < my_rows; rc += rows_per_chunk) {
-        // ---------------- phase A: scan + compact (warp-local) -------------------------------
-        int count = 0;  // warp-uniform
-        const int rce = min(rc + rows_per_chunk, my_rows);
-        for (int i = rc; i < rce; i++) {
-            const int row = warp + NWARP * i;
-            const int y = y0 + row % by, z = z0 + row / by;
-            const float dy = fm(fs((float)y, kp.y), uyf), dz = fm(fs((float)z, kp.z), uzf);
-            const float rem = r2 - (dy * dy + dz * dz);
-            if (rem < -1e-3f * r2) continue;  // whole row outside the sphere (conservative)
-            const float hx = sqrtf(fmaxf(rem, 0.0f)) * iux + 1.5f;
-            const int xa = max(x0, (int)floorf(kp.x - hx)), xb = min(x1, (int)ceilf(kp.x + hx));
-            for (int xs = xa; xs <= xb; xs += 32) {
-                const int x = xs + lane;
-                float sq, vb[3];
-                const bool ok = x <= xb && geom(x, y, z, sq, vb);
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok)
-                    seg[count + __popc(m & ((1u << lane) - 1u))] =
-                        (unsigned)(x - x0) | ((unsigned)(y - y0) << 10) | ((unsigned)(z - z0) << 20);
-                count += __popc(m);
+    // slab a: vb = (sl[a] * dxv + off_row[a]) with dxv = x - kp.x in voxels
+    float sl[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) sl[a] = Rt[3 * a] * uxf * bin_fctr;
+    for (int rc = 0; rc < my_rows; rc += 32) {
+        // ---------------- phase A: one row per lane ------------------------------------------
+        int cnt = 0, xa = 0, yy = 0, zz = 0;
+        if (rc + lane < my_rows) {
+            const int row = warp + NWARP * (rc + lane);
+            yy = y0 + row % by;
+            zz = z0 + row / by;
+            const float vy = ((float)yy - kp.y) * uyf, vz = ((float)zz - kp.z) * uzf;
+            const float rem = r2 - (vy * vy + vz * vz);
+            if (rem >= -1e-3f * r2) {
+                const float hx = sqrtf(fmaxf(rem, 0.0f)) * iux;
+                float lo = -hx, hi = hx;  // in voxels relative to kp.x
+                bool empty = false;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float off = (Rt[3 * a + 1] * vy + Rt[3 * a + 2] * vz + half) * bin_fctr;
+                    if (fabsf(sl[a]) < 1e-6f) {  // the slab does not depend on x
+                        empty = empty || off < -1e-3f || off > 4.001f;
+                    } else {
+                        const float t0 = (0.0f - off) / sl[a], t1 = (4.0f - off) / sl[a];
+                        lo = fmaxf(lo, fminf(t0, t1));
+                        hi = fminf(hi, fmaxf(t0, t1));
+                    }
+                }
+                if (!empty && lo <= hi + 1.0f) {
+                    // widen by one voxel each side: covers every rounding of the estimates above
+                    xa = max(x0, (int)floorf(kp.x + lo) - 1);
+                    const int xb = min(x1, (int)ceilf(kp.x + hi) + 1);
+                    cnt = max(xb - xa + 1, 0);
+                }
             }
         }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        rows[lane] = make_int4(incl - cnt, xa, yy, zz);
+        if (lane == 0) rows[32] = make_int4(total, 0, 0, 0);
         __syncwarp();
         // ---------------- phase B: per-voxel work ---------------------------------------------
-        // lane l owns the contiguous entries [l*L, l*L+L): its consecutive voxels are x
-        // neighbours (cache-friendly loads) while the 32 lanes sit L entries apart, i.e. in
-        // different spatial cells most of the time (few same-address atomics)
-        const int L = (count + 31) >> 5;
-        for (int k = 0; k < L; k++) {
-            const int e = lane * L + k;
-            if (e >= count) break;
-            const unsigned code = seg[e];
-            const int x = x0 + (int)(code & 1023u), y = y0 + (int)((code >> 10) & 1023u),
-                      z = z0 + (int)(code >> 20);
+        const int L = (total + 31) >> 5;
+        int idx = lane * L;
+        const int idx_end = min(idx + L, total);
+        int r = 0;
+        if (idx < idx_end) {  // last row whose first index is <= idx (empty rows share theirs)
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1)
+                if (rows[r + st].x <= idx) r += st;
+        }
+        int4 cur = rows[r];
+        int row_end = rows[r + 1].x;
+        int x = cur.y + (idx - cur.x);
+        for (int k = 0; k < L; k++, idx++, x++) {
+            if (idx >= idx_end) break;
+            while (idx >= row_end) {  // next non-empty row
+                r++;
+                cur = rows[r];
+                row_end = rows[r + 1].x;
+                x = cur.y;
+            }
+            const int y = cur.z, z = cur.w;
             float sq, vb[3];
-            geom(x, y, z, sq, vb);
+            if (!geom(x, y, z, sq, vb)) continue;
             const float *p = im + x + (size_t)y * ys + (size_t)z * zs;
             float g[3];
             g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
@@ -784,19 +837,52 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
             // fm(fm(mag_s, wgt), bary) == fm(fm(mag, wgt), bary) * 2^S (sift.c:1763-1765)
             const float mag_s = fm(mag, split ? fx_scale : 4294967296.0f);
             const bool small = mag_s < 2147480000.0f;  // |contribution| < 2^31 (bary <= 1 + eps)
+            // trilinear weights (1-dx | dx)(1-dy | dy)(1-dz | dz), products associated as in
+            // the reference: (x * y) * z
+            const float wx0 = fs(1.0f, dv[0]), wy0 = fs(1.0f, dv[1]), wz0 = fs(1.0f, dv[2]);
+            const float wxy[4] = {fm(wx0, wy0), fm(wx0, dv[1]), fm(dv[0], wy0), fm(dv[0], dv[1])};
+            // corners outside the 4x4x4 grid add nothing: they are steered to per-lane dummy
+            // slots so that the scatter stays branch-free.  ib <= 3, so a corner is outside iff
+            // it steps up along an axis whose base index is already 3.
+            const bool ex = ib[0] == 3, ey = ib[1] == 3, ez = ib[2] == 3;
+            int *const base_in = h_fx + 12 * (ib[0] + 4 * ib[1] + 16 * ib[2]);
+            int *const base_out = h_fx + S3D_DESC_NUMEL + lane;
+            const bool fast = split && small && FX_CARRY && bary[0] >= 0.0f && bary[1] >= 0.0f &&
+                              bary[2] >= 0.0f;
+            // shared-window byte addresses of the three vertex bins of the base cell, and the
+            // offset that moves them into this lane's dummy slots
+            const unsigned va0 = h_addr + 4u * (unsigned)(12 * (ib[0] + 4 * ib[1] + 16 * ib[2]) + i0);
+            const unsigned va1 = va0 + 4u * (unsigned)(i1 - i0), va2 = va0 + 4u * (unsigned)(i2 - i0);
+            const unsigned dummy_off =
+                4u * (unsigned)(S3D_DESC_NUMEL + lane - 12 * (ib[0] + 4 * ib[1] + 16 * ib[2]));
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-                const int cx = ib[0] + (c >> 2), cy = ib[1] + ((c >> 1) & 1), cz = ib[2] + (c & 1);
-                // corners outside the 4x4x4 grid add nothing: they are steered to per-lane
-                // dummy slots so that the scatter stays branch-free
-                const bool in = cx < 4 && cy < 4 && cz < 4;
-                int *cell = h_fx + (in ? 12 * (cx + 4 * cy + 16 * cz) : S3D_DESC_NUMEL + lane);
-                const float wgt = fm(fm((c >> 2) ? dv[0] : fs(1.0f, dv[0]),
-                                        ((c >> 1) & 1) ? dv[1] : fs(1.0f, dv[1])),
-                                     (c & 1) ? dv[2] : fs(1.0f, dv[2]));
+                const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
+                const bool in = !((dx && ex) || (dy && ey) || (dz && ez));
+                int *const cell = in ? base_in + 12 * (dx + 4 * dy + 16 * dz) : base_out;
+                const float wgt = fm(wxy[2 * dx + dy], dz ? dv[2] : wz0);
                 const float mw = fm(mag_s, wgt);
-                if (split && small) {
-                    if (FX_CARRY) {
+                if (fast) {
+                    // non-negative contributions (all but gradients within bary_eps outside an
+                    // edge): lo word += q with ONE ATOMS whose returned old value gives the
+                    // carry (q > ~old); hi word += 1 only then.  The three updates of a corner
+                    // are issued together so that their round trips overlap.  32-bit shared
+                    // addresses: one IADD per update (vertex address + corner offset).
+                    const unsigned coff = in ? 48u * (dx + 4 * dy + 16 * dz) : dummy_off;
+                    const unsigned a0 = va0 + coff, a1 = va1 + coff, a2 = va2 + coff;
+                    const unsigned q0 = __float2uint_rn(fm(mw, bary[0])),
+                                   q1 = __float2uint_rn(fm(mw, bary[1])),
+                                   q2 = __float2uint_rn(fm(mw, bary[2]));
+                    const unsigned o0 = atoms_add(a0, q0), o1 = atoms_add(a1, q1),
+                                   o2 = atoms_add(a2, q2);
+                    const bool c0 = q0 > ~o0, c1 = q1 > ~o1, c2 = q2 > ~o2;
+                    if (c0 | c1 | c2) {
+                        if (c0) atoms_inc(a0 + 4u * HSTRIDE);
+                        if (c1) atoms_inc(a1 + 4u * HSTRIDE);
+                        if (c2) atoms_inc(a2 + 4u * HSTRIDE);
+                    }
+                } else if (split && small) {
+                    if (FX_CARRY) {  // signed: hi += sign(q) + carry
                         int q[3], qh[3];
                         unsigned old[3];
                         int *bp[3];
