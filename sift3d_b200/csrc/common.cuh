@@ -108,6 +108,20 @@ struct s3d_engine {
     int kp_cap = 0;
     int nkp = 0;
 
+    // gradient volumes of the keypoint levels (keypoint.cu): float4 {gx, gy, gz, 0} per voxel,
+    // the central differences both the orientation and the descriptor kernels need -- one
+    // 16-byte gather per voxel instead of six 4-byte ones.  Optional (nullptr: scalar path).
+    std::vector<float4 *> grad;        // per gpyr level
+    std::vector<size_t> grad_cap;      // voxels allocated
+    float4 **d_level_gptrs = nullptr;  // device table (nullptr entries allowed)
+    bool grad_valid = false;           // volumes match the current pyramid contents
+
+    // orientation window-weight tables (keypoint.cu)
+    float *d_ori_pool = nullptr;
+    size_t ori_pool_cap = 0;
+    void *d_ori_tabs = nullptr;
+    size_t ori_tabs_cap = 0;
+
     // descriptor scratch
     s3d_keypoint *d_kp_in = nullptr;
     int kp_in_cap = 0;
@@ -185,3 +199,5 @@ int s3d_k_dense_rotate(s3d_engine *e, const float *d_smooth, int nx, int ny, int
                        double corner_thresh, float *d_out12);
 int s3d_k_dense_post(s3d_engine *e, float *d_desc12, const float *d_raw, size_t nvox);
 int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx);
+int s3d_gradients_prepare(s3d_engine *e);  // best effort: 0 also when memory is short
+void s3d_gradients_free(s3d_engine *e);

@@ -48,6 +48,7 @@ void s3d_free_pyramid(s3d_engine *e)
     e->d_level_zoff = nullptr;
     e->d_scalars = nullptr;
     e->noct = 0;
+    s3d_gradients_free(e);
     e->slab.clear();
     e->slab_own.clear();
     e->slab_need.clear();
@@ -177,7 +178,7 @@ void s3d_engine_destroy(s3d_engine *e)
     free_pyramid(e);
     void *ptrs[] = {e->im,    e->scratch[0], e->scratch[1], e->d_cand,  e->d_mask, e->d_blockcnt,
                     e->d_counter, e->d_kp_all, e->d_ok,       e->d_pos,   e->d_kp,   e->d_kp_in,
-                    e->d_desc, e->d_mesh, e->d_blur_dbg};
+                    e->d_desc, e->d_mesh, e->d_blur_dbg, e->d_ori_pool, e->d_ori_tabs};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &t : e->segtabs)
@@ -379,6 +380,7 @@ int s3d_build_pyramid(s3d_engine *e)
     if (e->noct < 1 || !e->im || (int)e->oct_taps.size() != e->nlev_g - 1)
         return s3d_fail(e, "s3d_build_pyramid: pyramid/filters/image not configured", cudaSuccess,
                         __FILE__, __LINE__);
+    e->grad_valid = false;
     if (!e->slab.empty()) return s3d_slab_build_pyramid(e);
     const LevelDev &base = e->g[0];
     if (base.g.nx != e->im_nx || base.g.ny != e->im_ny || base.g.nz != e->im_nz)
@@ -602,6 +604,7 @@ int s3d_single_level(s3d_engine *e, const float *host, int nx, int ny, int nz, s
     S3D_CUDA(e, cudaMemcpy(e->d_level_dims, dims, sizeof(dims), cudaMemcpyHostToDevice));
     S3D_CUDA(e, cudaMemcpy(e->d_level_units, fu, sizeof(fu), cudaMemcpyHostToDevice));
     S3D_CUDA(e, cudaMemcpy(e->d_level_scales, &scale, sizeof(double), cudaMemcpyHostToDevice));
+    e->grad_valid = false;
     if (ensure_im(e, nx, ny, nz)) return -1;
     if (upload_strided(e, e->im, host, nx, ny, nz, xs, ys, zs)) return -1;
     const float uf[3] = {(float)(1.0 / units[0]), (float)(1.0 / units[1]), (float)(1.0 / units[2])};
@@ -772,6 +775,7 @@ int s3d_pyramid_copy(s3d_engine *dst, const s3d_engine *src)
     for (size_t i = 0; i < d.size(); i++) d[i] = src->dog[i].g;
     if (s3d_pyramid_resize(dst, src->noct, src->K, g.data(), d.data())) return -1;
     DeviceGuard guard(dst->device);
+    dst->grad_valid = false;
     cudaStreamSynchronize(src->stream);
     for (size_t i = 0; i < g.size(); i++)
         S3D_CUDA(dst, cudaMemcpyPeerAsync(dst->g[i].d, dst->device, src->g[i].d, src->device,

@@ -15,6 +15,8 @@
 #include <cfloat>
 #include <cmath>
 
+static inline float __fdiv_rn_host(float u) { volatile float r = 1.0f / u; return r; }
+
 namespace {
 
 __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
@@ -172,6 +174,7 @@ struct PyrTable {
     int nlev_g;
     int first_level;
     const int *zoff;  // Z-slab tiling: global z of local plane 0, per level (nullptr: whole volumes)
+    const float4 *const *gptrs;  // gradient volumes per level (nullptr table or entries: none)
 };
 
 // Keypoint z coordinates are global; the level buffers of a Z-slab engine start at plane
@@ -234,6 +237,58 @@ __device__ __forceinline__ float expf_glibc(float x, const unsigned long long *t
     return (float)y;
 }
 
+// Second half of assign_eig_ori (sift.c:1424-1497): eigenvectors of the structure tensor,
+// eigenvalue-ratio and corner tests, sign-fixed rotation matrix.
+__device__ __forceinline__ bool orient_finish(double a00, double a01, double a02, double a11,
+                                              double a12, double a22, float wx, float wy, float wz,
+                                              double corner_thresh, float R[9], double &conf)
+{
+    bool accept = true;
+    conf = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = 0.0f;
+    const float wn2 = fa(fa(fm(wx, wx), fm(wy, wy)), fm(wz, wz));
+    if (wn2 < (float)1E-10) accept = false;  // ori_grad_thresh, sift.c:1426
+    if (accept) {
+        const double A[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
+        double Q[9], L[3];
+        eig3(A, Q, L);
+        if (fabs(__ddiv_rn(L[0], L[1])) > 0.90 || fabs(__ddiv_rn(L[1], L[2])) > 0.90)
+            accept = false;  // max_eig_ratio, sift.c:1440-1444
+        if (accept) {
+            double corner = DBL_MAX;
+            float v[2][3];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {  // sift.c:1448-1480
+                const int ei = 2 - k;
+                float vr0 = (float)Q[0 * 3 + ei], vr1 = (float)Q[1 * 3 + ei],
+                      vr2 = (float)Q[2 * 3 + ei];
+                const double d = (double)dot3(wx, vr0, wy, vr1, wz, vr2);
+                const float nv = __fsqrt_rn(fa(fa(fm(vr0, vr0), fm(vr1, vr1)), fm(vr2, vr2)));
+                const float nw = __fsqrt_rn(wn2);
+                const double cos_ang = __ddiv_rn(d, (double)fm(nv, nw));
+                corner = fmin(corner, fabs(cos_ang));
+                const float sgn = d > 0.0 ? 1.0f : -1.0f;
+                vr0 = fm(vr0, sgn);
+                vr1 = fm(vr1, sgn);
+                vr2 = fm(vr2, sgn);
+                R[0 * 3 + k] = vr0;
+                R[1 * 3 + k] = vr1;
+                R[2 * 3 + k] = vr2;
+                v[k][0] = vr0;
+                v[k][1] = vr1;
+                v[k][2] = vr2;
+            }
+            R[0 * 3 + 2] = fs(fm(v[0][1], v[1][2]), fm(v[0][2], v[1][1]));
+            R[1 * 3 + 2] = fs(fm(v[0][2], v[1][0]), fm(v[0][0], v[1][2]));
+            R[2 * 3 + 2] = fs(fm(v[0][0], v[1][1]), fm(v[0][1], v[1][0]));
+            conf = corner;
+            if (corner < corner_thresh) accept = false;  // sift.c:1340-1341
+        }
+    }
+    return accept;
+}
+
 // ---------------------------------------------------------------- orientation
 // assign_eig_ori + the corner threshold (sift.c:1336-1497) for one window centre, walked in
 // the reference's raster order so the f32 window gradient and the f64 structure tensor see
@@ -292,57 +347,124 @@ __device__ __forceinline__ bool orient_core(const float *__restrict__ im, int nx
             }
         }
     }
-    bool accept = true;
-    conf = 0.0;
-#pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = 0.0f;
-    const float wn2 = fa(fa(fm(wx, wx), fm(wy, wy)), fm(wz, wz));
-    if (wn2 < (float)1E-10) accept = false;  // ori_grad_thresh, sift.c:1426
-    if (accept) {
-        const double A[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
-        double Q[9], L[3];
-        eig3(A, Q, L);
-        if (fabs(__ddiv_rn(L[0], L[1])) > 0.90 || fabs(__ddiv_rn(L[1], L[2])) > 0.90)
-            accept = false;  // max_eig_ratio, sift.c:1440-1444
-        if (accept) {
-            double corner = DBL_MAX;
-            float v[2][3];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {  // sift.c:1448-1480
-                const int ei = 2 - k;
-                float vr0 = (float)Q[0 * 3 + ei], vr1 = (float)Q[1 * 3 + ei],
-                      vr2 = (float)Q[2 * 3 + ei];
-                const double d = (double)dot3(wx, vr0, wy, vr1, wz, vr2);
-                const float nv = __fsqrt_rn(fa(fa(fm(vr0, vr0), fm(vr1, vr1)), fm(vr2, vr2)));
-                const float nw = __fsqrt_rn(wn2);
-                const double cos_ang = __ddiv_rn(d, (double)fm(nv, nw));
-                corner = fmin(corner, fabs(cos_ang));
-                const float sgn = d > 0.0 ? 1.0f : -1.0f;
-                vr0 = fm(vr0, sgn);
-                vr1 = fm(vr1, sgn);
-                vr2 = fm(vr2, sgn);
-                R[0 * 3 + k] = vr0;
-                R[1 * 3 + k] = vr1;
-                R[2 * 3 + k] = vr2;
-                v[k][0] = vr0;
-                v[k][1] = vr1;
-                v[k][2] = vr2;
-            }
-            R[0 * 3 + 2] = fs(fm(v[0][1], v[1][2]), fm(v[0][2], v[1][1]));
-            R[1 * 3 + 2] = fs(fm(v[0][2], v[1][0]), fm(v[0][0], v[1][2]));
-            R[2 * 3 + 2] = fs(fm(v[0][0], v[1][1]), fm(v[0][1], v[1][0]));
-            conf = corner;
-            if (corner < corner_thresh) accept = false;  // sift.c:1340-1341
-        }
+    return orient_finish(a00, a01, a02, a11, a12, a22, wx, wy, wz, corner_thresh, R, conf);
+}
+
+// ---- window-weight tables for integer-centred candidates -----------------------------------
+// Every detector candidate of a level (o, s) sits on an integer voxel and uses the same sigma,
+// so the sphere test and the window weight expf(-0.5 * d^2 / sigma^2) (sift.c:1393-1401) depend
+// only on the integer offset (dx, dy, dz): they are tabulated once per level by k_orient_table
+// with exactly the arithmetic of orient_core (-1 marks offsets outside the sphere), which takes
+// the f64 division and the exp out of the per-candidate loop.
+struct OriTab {
+    int off;  // first entry in the table pool, -1 if the level has none
+    int rx, ry, rz;
+};
+
+__global__ void __launch_bounds__(256)
+    k_orient_table(const OriTab *__restrict__ tabs, PyrTable T, double sig_fctr,
+                   float *__restrict__ pool)
+{
+    __shared__ unsigned long long s_tab[32];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+    __syncthreads();
+    const int lv = blockIdx.y;
+    const OriTab t = tabs[lv];
+    if (t.off < 0) return;
+    const int wx = 2 * t.rx + 1, wy = 2 * t.ry + 1, wz = 2 * t.rz + 1;
+    const double sigma = sig_fctr * T.scales[lv];
+    const double r2 = (sigma * 3.0) * (sigma * 3.0), s2 = sigma * sigma;
+    const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wx * wy * wz;
+         i += gridDim.x * blockDim.x) {
+        const int ix = i % wx - t.rx, iy = (i / wx) % wy - t.ry, iz = i / (wx * wy) - t.rz;
+        const float dx = fm((float)ix, uxf), dy = fm((float)iy, uyf), dz = fm((float)iz, uzf);
+        const float sq = fa(fa(fm(dx, dx), fm(dy, dy)), fm(dz, dz));
+        float w = -1.0f;
+        if (!((double)sq > r2))
+            w = expf_glibc((float)__ddiv_rn(__dmul_rn(-0.5, (double)sq), s2), s_tab);
+        pool[t.off + i] = w;
     }
-    return accept;
+}
+
+// orient_core for an integer centre with a weight table: same voxels, same order, same values.
+__device__ __forceinline__ bool orient_core_tab(const float *__restrict__ im, int nx, int ny,
+                                                int nz, float uxf, float uyf, float uzf, int cx,
+                                                int cy, int cz, double sigma,
+                                                const float *__restrict__ tab, const OriTab t,
+                                                const float4 *__restrict__ gim,
+                                                double corner_thresh, float R[9], double &conf)
+{
+    const double win_radius = sigma * 3.0;
+    const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
+    int x0, x1, y0, y1, z0, z1;
+    sphere_bounds_d((float)cx, win_radius, uxf, nx, x0, x1);
+    sphere_bounds_d((float)cy, win_radius, uyf, ny, y0, y1);
+    sphere_bounds_d((float)cz, win_radius, uzf, nz, z0, z1);
+    // the table covers offsets up to +-r*; the loop bounds never exceed ceil(radius / unit)
+    x0 = max(x0, cx - t.rx), x1 = min(x1, cx + t.rx);
+    y0 = max(y0, cy - t.ry), y1 = min(y1, cy + t.ry);
+    z0 = max(z0, cz - t.rz), z1 = min(z1, cz + t.rz);
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    const int twx = 2 * t.rx + 1, twy = 2 * t.ry + 1;
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    float wx = 0.0f, wy = 0.0f, wz = 0.0f;
+    for (int z = z0; z <= z1; z++)
+        for (int y = y0; y <= y1; y++) {
+            const size_t roff = (size_t)y * ys + (size_t)z * zs;
+            const float *row = im + roff;
+            const float *trow = tab + ((size_t)(z - cz + t.rz) * twy + (y - cy + t.ry)) * twx + (t.rx - cx);
+            // A thread walks its window alone (the sums must see the reference's order), so
+            // its speed is set by load latency: fetch four voxels' weights and gradients
+            // before consuming them in order.
+            auto acc = [&](float w, float gx, float gy, float gz) {
+                const double dw = (double)w, gxd = gx, gyd = gy, gzd = gz;
+                a00 = __dadd_rn(a00, __dmul_rn(__dmul_rn(gxd, gxd), dw));
+                a01 = __dadd_rn(a01, __dmul_rn(__dmul_rn(gxd, gyd), dw));
+                a02 = __dadd_rn(a02, __dmul_rn(__dmul_rn(gxd, gzd), dw));
+                a11 = __dadd_rn(a11, __dmul_rn(__dmul_rn(gyd, gyd), dw));
+                a12 = __dadd_rn(a12, __dmul_rn(__dmul_rn(gyd, gzd), dw));
+                a22 = __dadd_rn(a22, __dmul_rn(__dmul_rn(gzd, gzd), dw));
+                wx = fa(wx, fm(gx, w));
+                wy = fa(wy, fm(gy, w));
+                wz = fa(wz, fm(gz, w));
+            };
+            if (gim) {
+                const float4 *grow = gim + roff;
+                for (int x = x0; x <= x1; x += 4) {
+                    float w[4];
+                    float4 g4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int xx = min(x + k, x1);
+                        w[k] = __ldg(trow + xx);
+                        g4[k] = __ldg(grow + xx);
+                        if (x + k > x1) w[k] = -1.0f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (w[k] >= 0.0f) acc(w[k], g4[k].x, g4[k].y, g4[k].z);
+                }
+            } else {
+                for (int x = x0; x <= x1; x++) {
+                    const float w = __ldg(trow + x);
+                    if (w < 0.0f) continue;  // outside the sphere
+                    const float *p = row + x;
+                    acc(w, fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux),
+                        fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy),
+                        fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz));
+                }
+            }
+        }
+    return orient_finish(a00, a01, a02, a11, a12, a22, wx, wy, wz, corner_thresh, R, conf);
 }
 
 // One thread per candidate.  Candidates adjacent in scan order share (o, s) and integer
 // centres, so the lanes of a warp walk identical offsets in lock step.
 __global__ void __launch_bounds__(128)
     k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
-             double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out)
+             double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out,
+             const OriTab *__restrict__ tabs, const float *__restrict__ pool)
 {
     __shared__ unsigned long long s_tab[32];
     if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
@@ -355,10 +477,20 @@ __global__ void __launch_bounds__(128)
     // (sift.c:1579)
     float R[9];
     double conf;
-    const bool accept =
-        orient_core(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
-                    T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2], c.x, c.y,
-                    local_z(T, lv, c.z), sig_fctr * c.sd, corner_thresh, s_tab, R, conf);
+    const float zl = local_z(T, lv, c.z);
+    bool accept;
+    // the table was built for sigma = sig_fctr * scale(level); detector candidates carry exactly
+    // that scale and integer centres (sift.c:1200-1204)
+    if (tabs && tabs[lv].off >= 0 && c.sd == T.scales[lv] && c.x == rintf(c.x) &&
+        c.y == rintf(c.y) && zl == rintf(zl))
+        accept = orient_core_tab(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
+                                 T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2],
+                                 (int)c.x, (int)c.y, (int)zl, sig_fctr * c.sd, pool + tabs[lv].off,
+                                 tabs[lv], T.gptrs ? T.gptrs[lv] : nullptr, corner_thresh, R, conf);
+    else
+        accept = orient_core(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
+                             T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2], c.x, c.y,
+                             zl, sig_fctr * c.sd, corner_thresh, s_tab, R, conf);
 #pragma unroll
     for (int k = 0; k < 9; k++) kps[i].R[k] = R[k];
     ok[i] = accept ? 1 : 0;
@@ -655,6 +787,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
     const float z_global = kp.z;
     kp.z = local_z(T, lv, kp.z);
     const float *__restrict__ im = T.ptrs[lv];
+    const float4 *__restrict__ gim = T.gptrs ? T.gptrs[lv] : nullptr;
     const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
     const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
     const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
@@ -806,11 +939,17 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
             const int y = cur.z, z = cur.w;
             float sq, vb[3];
             if (!geom(x, y, z, sq, vb)) continue;
-            const float *p = im + x + (size_t)y * ys + (size_t)z * zs;
+            const size_t voff = x + (size_t)y * ys + (size_t)z * zs;
             float g[3];
-            g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
-            g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
-            g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+            if (gim) {  // block-uniform: one 16-byte gather instead of six 4-byte ones
+                const float4 g4 = __ldg(gim + voff);
+                g[0] = g4.x, g[1] = g4.y, g[2] = g4.z;
+            } else {
+                const float *p = im + voff;
+                g[0] = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+                g[1] = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+                g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+            }
             // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument
             const float wgt_win = expf_glibc(__fdiv_rn(fm(-0.5f, sq), s2), s_tab);
             g[0] = fm(g[0], wgt_win);
@@ -1167,6 +1306,32 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------- gradient volumes
+// SIFT3D_IM_GET_GRAD (immacros.h:105-111) scaled by 1/units (IM_GET_GRAD_ISO, sift.c:150-155):
+// g = (0.5f * (v[+1] - v[-1])) * (1 / unit) per axis, f32, separately rounded -- the expression
+// both assign_eig_ori (sift.c:1385) and extract_descrip (sift.c:1882) evaluate per visit.
+__global__ void __launch_bounds__(256)
+    k_gradient(const float *__restrict__ im, int nx, int ny, int nz, float iux, float iuy,
+               float iuz, float4 *__restrict__ out)
+{
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % nx);
+        const size_t r = idx / nx;
+        const int y = (int)(r % ny), z = (int)(r / ny);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
+            const float *p = im + idx;
+            g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+            g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+            g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+        }
+        out[idx] = g;
+    }
+}
+
 PyrTable make_table(const s3d_engine *e)
 {
     PyrTable T;
@@ -1177,10 +1342,65 @@ PyrTable make_table(const s3d_engine *e)
     T.nlev_g = e->nlev_g;
     T.first_level = e->first_level;
     T.zoff = e->slab.empty() ? nullptr : e->d_level_zoff;
+    T.gptrs = e->grad_valid ? e->d_level_gptrs : nullptr;
     return T;
 }
 
 }  // namespace
+
+void s3d_gradients_free(s3d_engine *e)
+{
+    for (float4 *p : e->grad)
+        if (p) cudaFree(p);
+    e->grad.clear();
+    e->grad_cap.clear();
+    if (e->d_level_gptrs) cudaFree(e->d_level_gptrs);
+    e->d_level_gptrs = nullptr;
+    e->grad_valid = false;
+}
+
+// Gradient volumes for the keypoint levels s = 0..K-1 of the resident pyramid.  Best effort:
+// a level whose volume cannot be allocated keeps a null entry and the kernels gather scalars.
+int s3d_gradients_prepare(s3d_engine *e)
+{
+    if (e->grad_valid) return 0;
+    const int L = (int)e->g.size();
+    if (L == 0) return 0;
+    if ((int)e->grad.size() != L) {
+        s3d_gradients_free(e);
+        e->grad.assign(L, nullptr);
+        e->grad_cap.assign(L, 0);
+    }
+    if (!e->d_level_gptrs) S3D_CUDA(e, cudaMalloc(&e->d_level_gptrs, L * sizeof(float4 *)));
+    for (int lv = 0; lv < L; lv++) {
+        const int sidx = lv % e->nlev_g + e->first_level;
+        const LevelDev &l = e->g[lv];
+        const bool want = sidx >= 0 && sidx < e->K && l.d && l.n() > 0;
+        if (!want) continue;
+        if (e->grad_cap[lv] < l.n()) {
+            if (e->grad[lv]) cudaFree(e->grad[lv]);
+            e->grad[lv] = nullptr;
+            e->grad_cap[lv] = 0;
+            if (cudaMalloc(&e->grad[lv], l.n() * sizeof(float4)) != cudaSuccess) {
+                cudaGetLastError();  // out of memory: this level stays on the scalar path
+                e->grad[lv] = nullptr;
+                continue;
+            }
+            e->grad_cap[lv] = l.n();
+        }
+        const float ux = (float)l.g.ux, uy = (float)l.g.uy, uz = (float)l.g.uz;
+        const size_t want_blocks = (l.n() + 255) / 256;
+        const int grid = (int)std::min<size_t>(want_blocks, (size_t)e->num_sms * 32);
+        k_gradient<<<grid, 256, 0, e->stream>>>(l.d, l.g.nx, l.g.ny, l.g.nz, __fdiv_rn_host(ux),
+                                               __fdiv_rn_host(uy), __fdiv_rn_host(uz), e->grad[lv]);
+        S3D_LAUNCH_CHECK(e);
+    }
+    S3D_CUDA(e, cudaMemcpyAsync(e->d_level_gptrs, e->grad.data(), L * sizeof(float4 *),
+                                cudaMemcpyHostToDevice, e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->grad_valid = true;
+    return 0;
+}
 
 int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx)
 {
@@ -1256,7 +1476,56 @@ int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
     if (n <= 0) return 0;
     const PyrTable T = make_table(e);
     k_orient<<<(n + 127) / 128, 128, 0, e->stream>>>(d_kp, n, T, sig_fctr, corner_thresh, d_ok,
-                                                    d_conf);
+                                                    d_conf, nullptr, nullptr);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+// Window-weight tables for the keypoint levels s = 0..K-1 of every octave (see k_orient_table).
+static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr)
+{
+    const int L = e->noct * e->nlev_g;
+    std::vector<OriTab> tabs(L);
+    size_t total = 0;
+    for (int lv = 0; lv < L; lv++) {
+        OriTab &t = tabs[lv];
+        t.off = -1;
+        t.rx = t.ry = t.rz = 0;
+        const int sidx = lv % e->nlev_g + e->first_level;  // level index s
+        if (sidx < 0 || sidx >= e->K) continue;
+        const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
+        const double rad = sig_fctr * g.scale * 3.0;
+        const double r[3] = {rad / (double)(float)g.ux, rad / (double)(float)g.uy,
+                             rad / (double)(float)g.uz};
+        if (!(r[0] < 200 && r[1] < 200 && r[2] < 200)) continue;  // absurd scales: direct path
+        t.rx = (int)ceil(r[0]) + 1;
+        t.ry = (int)ceil(r[1]) + 1;
+        t.rz = (int)ceil(r[2]) + 1;
+        const size_t n = (size_t)(2 * t.rx + 1) * (2 * t.ry + 1) * (2 * t.rz + 1);
+        if (total + n > ((size_t)1 << 27)) continue;
+        t.off = (int)total;
+        total += n;
+    }
+    if (total == 0) return 1;
+    if (total > e->ori_pool_cap) {
+        if (e->d_ori_pool) cudaFree(e->d_ori_pool);
+        e->d_ori_pool = nullptr;
+        e->ori_pool_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->d_ori_pool, total * sizeof(float)));
+        e->ori_pool_cap = total;
+    }
+    if ((size_t)L > e->ori_tabs_cap) {
+        if (e->d_ori_tabs) cudaFree(e->d_ori_tabs);
+        e->d_ori_tabs = nullptr;
+        e->ori_tabs_cap = 0;
+        S3D_CUDA(e, cudaMalloc(&e->d_ori_tabs, L * sizeof(OriTab)));
+        e->ori_tabs_cap = L;
+    }
+    S3D_CUDA(e, cudaMemcpyAsync(e->d_ori_tabs, tabs.data(), L * sizeof(OriTab), cudaMemcpyHostToDevice,
+                                e->stream));
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));  // `tabs` is a stack-owned host buffer
+    k_orient_table<<<dim3(64, L), 256, 0, e->stream>>>(static_cast<const OriTab *>(e->d_ori_tabs), T,
+                                                      sig_fctr, e->d_ori_pool);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -1281,7 +1550,16 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
     }
     if (s3d_pack_candidates(e, e->d_kp_all)) return -1;
     // ori_sig_fctr = 1.5 (sift.c:51, 1281)
-    if (s3d_k_orient_list(e, e->d_kp_all, n, 1.5, corner_thresh, e->d_ok, nullptr)) return -1;
+    {
+        if (s3d_gradients_prepare(e)) return -1;
+        const PyrTable T = make_table(e);
+        const int trc = build_orient_tables(e, T, 1.5);
+        if (trc < 0) return -1;
+        k_orient<<<(n + 127) / 128, 128, 0, e->stream>>>(
+            e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
+            trc == 0 ? static_cast<const OriTab *>(e->d_ori_tabs) : nullptr, e->d_ori_pool);
+        S3D_LAUNCH_CHECK(e);
+    }
     k_flag_scan<<<1, 1024, 0, e->stream>>>(e->d_ok, n, e->d_pos, e->d_counter);
     S3D_LAUNCH_CHECK(e);
     k_compact_keypoints<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_kp_all, e->d_ok, e->d_pos, n,
@@ -1294,6 +1572,7 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
 {
     if (n <= 0) return 0;
     if (!e->have_mesh) return s3d_fail(e, "mesh not set", cudaSuccess, __FILE__, __LINE__);
+    if (s3d_gradients_prepare(e)) return -1;
     const PyrTable T = make_table(e);
     // v2 packs window offsets in 10 bits per axis; a window wider than 1023 voxels (absurd
     // scales) takes the simple kernel
