@@ -435,12 +435,12 @@ __device__ __forceinline__ bool orient_core_tab(const float *__restrict__ im, in
                     float w[4];
                     float4 g4[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int xx = min(x + k, x1);
-                        w[k] = __ldg(trow + xx);
-                        g4[k] = __ldg(grow + xx);
-                        if (x + k > x1) w[k] = -1.0f;
-                    }
+                    for (int k = 0; k < 4; k++) w[k] = x + k <= x1 ? __ldg(trow + x + k) : -1.0f;
+                    // gradients only inside the sphere (48 % of the box is outside): the window
+                    // traffic, 16 B per visited voxel from L2, is what bounds this kernel
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        g4[k] = w[k] >= 0.0f ? __ldg(grow + x + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if (w[k] >= 0.0f) acc(w[k], g4[k].x, g4[k].y, g4[k].z);
@@ -461,14 +461,20 @@ __device__ __forceinline__ bool orient_core_tab(const float *__restrict__ im, in
 
 // One thread per candidate.  Candidates adjacent in scan order share (o, s) and integer
 // centres, so the lanes of a warp walk identical offsets in lock step.
-__global__ void __launch_bounds__(128)
+// TAB = true: detector candidates only (integer centres, sd == level scale, a table for every
+// keypoint level -- the launcher guarantees it); a separate instantiation so that the literal
+// path's f64 exp does not cost the fast one its occupancy.
+template <bool TAB>
+__global__ void __launch_bounds__(128, TAB ? 8 : 4)
     k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
              double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out,
              const OriTab *__restrict__ tabs, const float *__restrict__ pool)
 {
     __shared__ unsigned long long s_tab[32];
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
-    __syncthreads();
+    if (!TAB) {
+        if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const s3d_keypoint c = kps[i];
@@ -479,10 +485,7 @@ __global__ void __launch_bounds__(128)
     double conf;
     const float zl = local_z(T, lv, c.z);
     bool accept;
-    // the table was built for sigma = sig_fctr * scale(level); detector candidates carry exactly
-    // that scale and integer centres (sift.c:1200-1204)
-    if (tabs && tabs[lv].off >= 0 && c.sd == T.scales[lv] && c.x == rintf(c.x) &&
-        c.y == rintf(c.y) && zl == rintf(zl))
+    if (TAB)
         accept = orient_core_tab(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
                                  T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2],
                                  (int)c.x, (int)c.y, (int)zl, sig_fctr * c.sd, pool + tabs[lv].off,
@@ -1475,8 +1478,8 @@ int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
 {
     if (n <= 0) return 0;
     const PyrTable T = make_table(e);
-    k_orient<<<(n + 127) / 128, 128, 0, e->stream>>>(d_kp, n, T, sig_fctr, corner_thresh, d_ok,
-                                                    d_conf, nullptr, nullptr);
+    k_orient<false><<<(n + 127) / 128, 128, 0, e->stream>>>(d_kp, n, T, sig_fctr, corner_thresh,
+                                                           d_ok, d_conf, nullptr, nullptr);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -1497,12 +1500,12 @@ static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr
         const double rad = sig_fctr * g.scale * 3.0;
         const double r[3] = {rad / (double)(float)g.ux, rad / (double)(float)g.uy,
                              rad / (double)(float)g.uz};
-        if (!(r[0] < 200 && r[1] < 200 && r[2] < 200)) continue;  // absurd scales: direct path
+        if (!(r[0] < 200 && r[1] < 200 && r[2] < 200)) return 1;  // absurd scales: literal path
         t.rx = (int)ceil(r[0]) + 1;
         t.ry = (int)ceil(r[1]) + 1;
         t.rz = (int)ceil(r[2]) + 1;
         const size_t n = (size_t)(2 * t.rx + 1) * (2 * t.ry + 1) * (2 * t.rz + 1);
-        if (total + n > ((size_t)1 << 27)) continue;
+        if (total + n > ((size_t)1 << 27)) return 1;
         t.off = (int)total;
         total += n;
     }
@@ -1555,9 +1558,13 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
         const PyrTable T = make_table(e);
         const int trc = build_orient_tables(e, T, 1.5);
         if (trc < 0) return -1;
-        k_orient<<<(n + 127) / 128, 128, 0, e->stream>>>(
-            e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
-            trc == 0 ? static_cast<const OriTab *>(e->d_ori_tabs) : nullptr, e->d_ori_pool);
+        if (trc == 0)  // every keypoint level has a table
+            k_orient<true><<<(n + 127) / 128, 128, 0, e->stream>>>(
+                e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
+                static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool);
+        else
+            k_orient<false><<<(n + 127) / 128, 128, 0, e->stream>>>(
+                e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr, nullptr, nullptr);
         S3D_LAUNCH_CHECK(e);
     }
     k_flag_scan<<<1, 1024, 0, e->stream>>>(e->d_ok, n, e->d_pos, e->d_counter);
