@@ -115,11 +115,29 @@ template <int AXIS>
 __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src,
                                                    float *__restrict__ dst, int nx, int ny,
                                                    int nz, int nc, const TapSet taps, float uf,
-                                                   int zoff, int nbuf, int gbase, int nglob)
+                                                   int zoff, int nbuf, int gbase, int nglob,
+                                                   int dyadic)
 {
     const size_t total = (size_t)nx * ny * nz * nc;
     const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nglob);
     if (AXIS != 2) nbuf = n, gbase = 0;
+    // Dyadic tap spacing (uf = 2^-k, every pyramid octave with power-of-two units): for an
+    // interior voxel i the sample coordinate c = i - d*uf is exact in f32, so (int)c = i +
+    // floor(-d*uf) and frac = c - (int)c = frac(-d*uf) do not depend on i -- one table entry
+    // per tap replaces the per-tap coordinate arithmetic, with bit-identical results.
+    __shared__ int s_off[S3D_MAX_TAPS];
+    __shared__ float s_f[S3D_MAX_TAPS], s_omf[S3D_MAX_TAPS];
+    if (dyadic) {
+        for (int t = threadIdx.x; t < taps.width; t += blockDim.x) {
+            const float rel = -__fmul_rn((float)(t - taps.width / 2), uf);
+            const float fl = floorf(rel);
+            const float f = __fsub_rn(rel, fl);
+            s_off[t] = (int)fl;
+            s_f[t] = f;
+            s_omf[t] = __fsub_rn(1.0f, f);
+        }
+        __syncthreads();
+    }
     const size_t st = AXIS == 0 ? (size_t)nc : (AXIS == 1 ? (size_t)nc * nx : (size_t)nc * nx * ny);
     const int hw = taps.width / 2;
     const int dim_end = n - 1;
@@ -136,7 +154,14 @@ __global__ void __launch_bounds__(256) k_conv_axis(const float *__restrict__ src
         const int i = AXIS == 0 ? x : (AXIS == 1 ? y : z + zoff + gbase);  // global index
         const float *line = src + (idx - (size_t)(AXIS == 2 ? z : i) * st);
         float acc = 0.0f;
-        if (i >= start && i <= end) {
+        if (dyadic && i >= start && i <= end) {
+            const float *base = line + (size_t)(i - gbase) * st;
+            for (int t = 0; t < taps.width; t++) {
+                const float *p = base + (ptrdiff_t)s_off[t] * (ptrdiff_t)st;
+                const float v = __fadd_rn(__fmul_rn(s_omf[t], __ldg(p)), __fmul_rn(s_f[t], __ldg(p + st)));
+                acc = __fadd_rn(acc, __fmul_rn(taps.t[t], v));
+            }
+        } else if (i >= start && i <= end) {
             float c = (float)i;  // carried across taps (imutil.c:2335-2350)
             for (int d = -hw; d <= hw; d++) {
                 const float step = __fmul_rn((float)d, uf);
@@ -372,6 +397,15 @@ inline size_t head_of(size_t n, const void *a, const void *b = nullptr, const vo
     return std::min(n, ((16 - ma) & 15) / 4);
 }
 
+// uf == 2^-k (k >= 0) and every coordinate i - d*uf, i < n, exact in f32
+inline int is_dyadic(float uf, int n)
+{
+    int ex;
+    if (!(uf > 0.0f) || frexpf(uf, &ex) != 0.5f || ex > 1) return 0;  // uf = 2^(ex-1)
+    const int k = 1 - ex;
+    return k <= 20 && (long long)n < (1ll << (24 - k));
+}
+
 inline int grid_for(const s3d_engine *e, size_t work_items, int block, int per_sm)
 {
     const size_t want = (work_items + block - 1) / block;
@@ -424,13 +458,13 @@ int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int 
     if (s3d_ensure_scratch(e, total)) return -1;
     const int grid = grid_for(e, total, 256, 16);
     k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0],
-                                               0, nz, 0, nz);
+                                               0, nz, 0, nz, is_dyadic(uf[0], nx));
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
-                                               taps, uf[1], 0, nz, 0, nz);
+                                               taps, uf[1], 0, nz, 0, nz, is_dyadic(uf[1], ny));
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2],
-                                               0, nz, 0, nz);
+                                               0, nz, 0, nz, is_dyadic(uf[2], nz));
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -460,14 +494,14 @@ int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int n
     if (s3d_ensure_scratch(e, sub)) return -1;
     const int grid = grid_for(e, sub, 256, 16);
     k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src + plane * p0, e->scratch[0], nx, ny, p1 - p0, 1,
-                                               taps, uf[0], 0, 0, 0, 0);
+                                               taps, uf[0], 0, 0, 0, 0, is_dyadic(uf[0], nx));
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, p1 - p0, 1,
-                                               taps, uf[1], 0, 0, 0, 0);
+                                               taps, uf[1], 0, 0, 0, 0, is_dyadic(uf[1], ny));
     S3D_LAUNCH_CHECK(e);
     k_conv_axis<2><<<grid_for(e, plane * (size_t)(ze - zb), 256, 16), 256, 0, e->stream>>>(
         e->scratch[1], dst + plane * zb, nx, ny, ze - zb, 1, taps, uf[2], zb - p0, p1 - p0,
-        gz0 + p0, nz_glob);
+        gz0 + p0, nz_glob, is_dyadic(uf[2], nz_glob));
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
