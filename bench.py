@@ -367,6 +367,28 @@ def main():
     # max over ranks
     ms_dev, ms_e2e = sdist.max_over_ranks([ms_dev, ms_e2e], device=dev)
 
+    # ---- stage split of one device-resident step (untimed extra pass, rank 0, informational) --
+    stages = None
+    if rank == 0:
+        cu.s3d_engine_sync.argtypes = [C.c_void_p]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        nc_, nk_ = C.c_int(0), C.c_int(0)
+        cu.s3d_image_from_device(eng, vol_dev.data_ptr(), n, n, n)
+        evs[0].record(stream)
+        cu.s3d_build_pyramid(eng)
+        evs[1].record(stream)
+        cu.s3d_detect_extrema(eng, s.s.peak_thresh, C.byref(nc_))
+        evs[2].record(stream)
+        cu.s3d_assign_orientations(eng, s.s.corner_thresh, C.byref(nk_))
+        evs[3].record(stream)
+        if nk_.value > 0:
+            cu.s3d_extract_descriptors_device(eng, cu.s3d_device_keypoints(eng), nk_.value,
+                                              desc_dev.data_ptr())
+        evs[4].record(stream)
+        torch.cuda.synchronize()
+        names = ["pyramid+dog", "extrema", "orientation(+gradients)", "descriptors"]
+        stages = {nm: round(evs[i].elapsed_time(evs[i + 1]), 3) for i, nm in enumerate(names)}
+
     # ---- roofline of the separable Gaussian (rank 0) ---------------------------------------
     roof = None
     if rank == 0:
@@ -428,6 +450,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if stages is not None:
+            out["stages_ms"] = stages
         if roof is not None:
             out["roofline"] = roof
         if cpu is not None:
