@@ -1316,23 +1316,19 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_gradient(const float *__restrict__ im, int nx, int ny, int nz, float iux, float iuy,
                float iuz, float4 *__restrict__ out)
-{
-    const size_t total = (size_t)nx * ny * nz;
+{   // grid: (ceil(nx / 256), ny, nz) -- one voxel per thread, no index division
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= nx) return;
     const size_t ys = nx, zs = (size_t)nx * ny;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % nx);
-        const size_t r = idx / nx;
-        const int y = (int)(r % ny), z = (int)(r / ny);
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
-            const float *p = im + idx;
-            g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
-            g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
-            g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
-        }
-        out[idx] = g;
+    const size_t idx = x + y * ys + z * zs;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
+        const float *p = im + idx;
+        g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+        g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+        g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
     }
+    out[idx] = g;
 }
 
 PyrTable make_table(const s3d_engine *e)
@@ -1392,10 +1388,15 @@ int s3d_gradients_prepare(s3d_engine *e)
             e->grad_cap[lv] = l.n();
         }
         const float ux = (float)l.g.ux, uy = (float)l.g.uy, uz = (float)l.g.uz;
-        const size_t want_blocks = (l.n() + 255) / 256;
-        const int grid = (int)std::min<size_t>(want_blocks, (size_t)e->num_sms * 32);
-        k_gradient<<<grid, 256, 0, e->stream>>>(l.d, l.g.nx, l.g.ny, l.g.nz, __fdiv_rn_host(ux),
-                                               __fdiv_rn_host(uy), __fdiv_rn_host(uz), e->grad[lv]);
+        if (l.g.ny > 65535 || l.g.nz > 65535) {  // grid.y / grid.z limits: scalar path
+            cudaFree(e->grad[lv]);
+            e->grad[lv] = nullptr;
+            e->grad_cap[lv] = 0;
+            continue;
+        }
+        k_gradient<<<dim3((l.g.nx + 255) / 256, l.g.ny, l.g.nz), 256, 0, e->stream>>>(
+            l.d, l.g.nx, l.g.ny, l.g.nz, __fdiv_rn_host(ux), __fdiv_rn_host(uy), __fdiv_rn_host(uz),
+            e->grad[lv]);
         S3D_LAUNCH_CHECK(e);
     }
     S3D_CUDA(e, cudaMemcpyAsync(e->d_level_gptrs, e->grad.data(), L * sizeof(float4 *),
