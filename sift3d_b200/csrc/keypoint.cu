@@ -1394,7 +1394,8 @@ int s3d_gradients_prepare(s3d_engine *e)
             e->grad_cap[lv] = 0;
             continue;
         }
-        k_gradient<<<dim3((l.g.nx + 255) / 256, l.g.ny, l.g.nz), 256, 0, e->stream>>>(
+        const int bdx = l.g.nx >= 256 ? 256 : ((l.g.nx + 31) / 32) * 32;
+        k_gradient<<<dim3((l.g.nx + bdx - 1) / bdx, l.g.ny, l.g.nz), bdx, 0, e->stream>>>(
             l.d, l.g.nx, l.g.ny, l.g.nz, __fdiv_rn_host(ux), __fdiv_rn_host(uy), __fdiv_rn_host(uz),
             e->grad[lv]);
         S3D_LAUNCH_CHECK(e);
