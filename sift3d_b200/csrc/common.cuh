@@ -74,6 +74,7 @@ struct s3d_engine {
     int blur_mode = 0;
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
+    int opt_desc_path = 0;  // test hook: force a fixed-point path of k_descriptor2 (0 = automatic)
     double blur_w[4] = {1.05, 1.10, 1.05, 1.10};  // per-plane cost of edge columns (left,right,top,bottom)
     int opt_blur_flags = 0;  // timing experiments only (results wrong when non-zero)
 

@@ -828,6 +828,11 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
         const float support = 8.0f * hist_width * hist_width * hist_width * iux * iuy * iuz;
         split = ex <= 31 && ex >= -60 && (FX_CARRY || support * 1.25f + 512.0f < 32768.0f);
     }
+    // test hook (s3d_set_option "desc_path"): 1 = signed general path, 2 = large-contribution
+    // path, 3 = legacy 2^-32 / 64-bit carry path -- all must agree with the default
+    const int force_path = icos_fast >> 1;
+    icos_fast &= 1;
+    if (force_path == 3) split = false;
     if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
     load_faces(s_face, s_lut, M);
     __syncthreads();
@@ -978,7 +983,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
             // mag * 2^S: scaling by a power of two commutes with every rounding below, so
             // fm(fm(mag_s, wgt), bary) == fm(fm(mag, wgt), bary) * 2^S (sift.c:1763-1765)
             const float mag_s = fm(mag, split ? fx_scale : 4294967296.0f);
-            const bool small = mag_s < 2147480000.0f;  // |contribution| < 2^31 (bary <= 1 + eps)
+            const bool small = mag_s < 2147480000.0f && force_path != 2;  // |contribution| < 2^31
             // trilinear weights (1-dx | dx)(1-dy | dy)(1-dz | dz), products associated as in
             // the reference: (x * y) * z
             const float wx0 = fs(1.0f, dv[0]), wy0 = fs(1.0f, dv[1]), wz0 = fs(1.0f, dv[2]);
@@ -989,8 +994,8 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
             const bool ex = ib[0] == 3, ey = ib[1] == 3, ez = ib[2] == 3;
             int *const base_in = h_fx + 12 * (ib[0] + 4 * ib[1] + 16 * ib[2]);
             int *const base_out = h_fx + S3D_DESC_NUMEL + lane;
-            const bool fast = split && small && FX_CARRY && bary[0] >= 0.0f && bary[1] >= 0.0f &&
-                              bary[2] >= 0.0f;
+            const bool fast = split && small && FX_CARRY && force_path == 0 && bary[0] >= 0.0f &&
+                              bary[1] >= 0.0f && bary[2] >= 0.0f;
             // shared-window byte addresses of the three vertex bins of the base cell, and the
             // offset that moves them into this lane's dummy slots
             const unsigned va0 = h_addr + 4u * (unsigned)(12 * (ib[0] + 4 * ib[1] + 16 * ib[2]) + i0);
@@ -1590,7 +1595,7 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
                                                         e->opt_icos_fast);
     else
         k_descriptor2<<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
-                                                          e->opt_icos_fast);
+                                                          (e->opt_icos_fast & 1) | (e->opt_desc_path << 1));
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

@@ -276,3 +276,32 @@ def test_full_size_properties(b200_lib):
     assert np.abs(nrm - 1).max() < 1e-5 and d1["hists"].min() >= 0
     R = kp1["R"].astype(np.float64)
     assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-3
+
+
+def test_descriptor_fixed_point_paths_agree(b200_lib):
+    """The descriptor kernel's fallback accumulation paths (signed general, large-contribution,
+    legacy 2^-32 with 64-bit carry) are exact integer arithmetic like the default one: forced
+    through the `desc_path` test hook they must reproduce its descriptors (bit for bit at the
+    same scale; to f32 rounding for the 2^-32 variant)."""
+    from sift3d_b200 import capi
+    from sift3d_b200.volumes import blob_volume
+    vol = blob_volume((56, 60, 64), seed=17)
+    cu = C.CDLL(str(capi.CUDA_LIB))
+    cu.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    b200_lib.lib.sift3d_b200_engine.restype = C.c_void_p
+    b200_lib.lib.sift3d_b200_engine.argtypes = [C.POINTER(capi.SIFT3D)]
+    with capi.Sift3D(b200_lib) as s:
+        kp = s.detect_keypoints(vol)
+        assert len(kp) > 20
+        eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+        base = s.extract_descriptors()["hists"].copy()
+        try:
+            for path in (1, 2, 3):
+                assert cu.s3d_set_option(eng, b"desc_path", path) == 0
+                d = s.extract_descriptors()["hists"]
+                if path < 3:
+                    assert np.array_equal(d, base), path
+                else:
+                    assert rel_l2(d, base).max() <= 1e-6
+        finally:
+            cu.s3d_set_option(eng, b"desc_path", 0)
