@@ -244,10 +244,14 @@ __global__ void __launch_bounds__(256) k_dog(const float *__restrict__ a,
 }
 
 // ---------------------------------------------------------------- extrema
-// Pass A: one thread per voxel of the octave, all K keypoint levels at once.
-// Emits a bit mask (scan order = linear voxel index) and per-block counts per
-// level, so that pass C can compact in the reference's (o, s, z, y, x) order.
-#define EXT_BLOCK 1024
+// Pass A: every block scans EXT_CHUNK consecutive voxels of the octave (linear index = scan
+// order), all K keypoint levels; a warp handles 32 consecutive voxels per step and lane 0 writes
+// their hit mask.  Emits the bit masks and per-block counts per level, so that pass C can compact
+// in the reference's (o, s, z, y, x) order.  The centre values of EXT_UNROLL steps x K levels are
+// loaded before any test (independent loads in flight; the tests themselves are rare-path).
+#define EXT_BLOCK 256
+#define EXT_CHUNK 8192  // voxels per block = 256 mask words
+#define EXT_UNROLL 4
 #define EXT_MAX_LEVELS 16
 
 struct ExtLevels {
@@ -256,52 +260,89 @@ struct ExtLevels {
     int K;
 };
 
+__device__ __forceinline__ bool ext_test(const ExtLevels &L, int s, size_t idx, float v, float thr,
+                                         size_t ys, size_t zs)
+{
+    if (!(v > thr || v < -thr)) return false;
+    const float *cur = L.dog[s + 1] + idx;
+    const float p = __ldg(L.dog[s] + idx), q = __ldg(L.dog[s + 2] + idx);
+    const float a0 = __ldg(cur + 1), a1 = __ldg(cur - 1), a2 = __ldg(cur + ys), a3 = __ldg(cur - ys),
+                a4 = __ldg(cur - zs), a5 = __ldg(cur + zs);
+    return (v > p && v > a0 && v > a1 && v > a2 && v > a3 && v > a4 && v > a5 && v > q) ||
+           (v < p && v < a0 && v < a1 && v < a2 && v < a3 && v < a4 && v < a5 && v < q);
+}
+
+template <int KT>  // KT > 0: K == KT known at compile time; KT == 0: any K <= EXT_MAX_LEVELS
 __global__ void __launch_bounds__(EXT_BLOCK)
     k_extrema_mark(const ExtLevels L, int nx, int ny, int nz, double peak_thresh,
                    unsigned *__restrict__ mask, int *__restrict__ blockcnt, int nblocks,
                    size_t words_per_level)
 {
+    const int K = KT > 0 ? KT : L.K;
+    constexpr int KA = KT > 0 ? KT : EXT_MAX_LEVELS;
     const size_t total = (size_t)nx * ny * nz;
-    const size_t idx = (size_t)blockIdx.x * EXT_BLOCK + threadIdx.x;
     const size_t ys = nx, zs = (size_t)nx * ny;
-    bool interior = false;
-    if (idx < total) {
-        const int x = (int)(idx % nx);
-        const size_t r = idx / nx;
-        const int y = (int)(r % ny);
-        const int z = (int)(r / ny);
-        interior = x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2;
-    }
-    __shared__ int s_cnt[32];
-    for (int s = 0; s < L.K; s++) {
-        bool hit = false;
-        if (interior) {
-            // thr = (float)(peak_thresh * dogmax), sift.c:1169
-            const float thr = (float)(peak_thresh * (double)__uint_as_float(L.maxbits[s + 1]));
-            const float *cur = L.dog[s + 1] + idx;
-            const float v = __ldg(cur);
-            if (v > thr || v < -thr) {
-                const float p = __ldg(L.dog[s] + idx), q = __ldg(L.dog[s + 2] + idx);
-                const float a0 = __ldg(cur + 1), a1 = __ldg(cur - 1), a2 = __ldg(cur + ys),
-                            a3 = __ldg(cur - ys), a4 = __ldg(cur - zs), a5 = __ldg(cur + zs);
-                hit = (v > p && v > a0 && v > a1 && v > a2 && v > a3 && v > a4 && v > a5 && v > q) ||
-                      (v < p && v < a0 && v < a1 && v < a2 && v < a3 && v < a4 && v < a5 && v < q);
+    const size_t base = (size_t)blockIdx.x * EXT_CHUNK;
+    __shared__ int s_cnt[EXT_MAX_LEVELS];
+    if (threadIdx.x < EXT_MAX_LEVELS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    float thr[KA];
+#pragma unroll
+    for (int s = 0; s < KA; s++)  // thr = (float)(peak_thresh * dogmax), sift.c:1169
+        thr[s] = s < K ? (float)(peak_thresh * (double)__uint_as_float(L.maxbits[s + 1])) : 0.0f;
+    int cnt[KA];
+#pragma unroll
+    for (int s = 0; s < KA; s++) cnt[s] = 0;
+    for (int it = 0; it < EXT_CHUNK / EXT_BLOCK; it += EXT_UNROLL) {
+        size_t idx[EXT_UNROLL];
+        bool interior[EXT_UNROLL];
+        float v[EXT_UNROLL][KA];
+#pragma unroll
+        for (int u = 0; u < EXT_UNROLL; u++) {
+            idx[u] = base + (size_t)(it + u) * EXT_BLOCK + threadIdx.x;
+            interior[u] = false;
+            if (idx[u] < total) {
+                int x, y, z;
+                if (total < 0xffffffffull) {  // 32-bit divisions
+                    const unsigned i32 = (unsigned)idx[u];
+                    const unsigned r = i32 / (unsigned)nx;
+                    x = (int)(i32 - r * (unsigned)nx);
+                    z = (int)(r / (unsigned)ny);
+                    y = (int)(r - (unsigned)z * (unsigned)ny);
+                } else {
+                    x = (int)(idx[u] % nx);
+                    const size_t r = idx[u] / nx;
+                    y = (int)(r % ny);
+                    z = (int)(r / ny);
+                }
+                interior[u] = x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2;
+            }
+#pragma unroll
+            for (int s = 0; s < KA; s++)
+                v[u][s] = (interior[u] && s < K) ? __ldg(L.dog[s + 1] + idx[u]) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < EXT_UNROLL; u++) {
+            if (base + (size_t)(it + u) * EXT_BLOCK >= total) break;  // block-uniform
+#pragma unroll
+            for (int s = 0; s < KA; s++) {
+                if (s >= K) break;
+                const bool hit = interior[u] && ext_test(L, s, idx[u], v[u][s], thr[s], ys, zs);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if ((threadIdx.x & 31) == 0) {
+                    mask[(size_t)s * words_per_level + (idx[u] >> 5)] = m;
+                    cnt[s] += __popc(m);
+                }
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if ((threadIdx.x & 31) == 0) {
-            mask[(size_t)s * words_per_level + (idx >> 5)] = m;
-            s_cnt[threadIdx.x >> 5] = __popc(m);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int c = s_cnt[threadIdx.x];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (threadIdx.x == 0) blockcnt[(size_t)s * nblocks + blockIdx.x] = c;
-        }
-        __syncthreads();
     }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int s = 0; s < KA; s++)
+            if (s < K && cnt[s]) atomicAdd(&s_cnt[s], cnt[s]);
+    }
+    __syncthreads();
+    if (threadIdx.x < K) blockcnt[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
 // Pass B: exclusive scan of the per-block counts, level after level, continuing
@@ -345,36 +386,35 @@ __global__ void __launch_bounds__(1024) k_extrema_scan(int *__restrict__ blockcn
     if (threadIdx.x == 0) counter[0] = s_run;
 }
 
-// Pass C: ordered scatter of the marked voxels.
+// Pass C: ordered scatter of the marked voxels.  One thread per mask word; a block covers the
+// EXT_CHUNK voxels (EXT_BLOCK words) of one pass-A block, whose offset pass B left in blockoff.
 __global__ void __launch_bounds__(EXT_BLOCK)
     k_extrema_emit(const unsigned *__restrict__ mask, const int *__restrict__ blockoff, int nblocks,
                    size_t words_per_level, int K, int o, int nx, int ny, int nz, int zbase,
                    Candidate *__restrict__ cand, int cap)
 {
     const size_t total = (size_t)nx * ny * nz;
-    const size_t idx = (size_t)blockIdx.x * EXT_BLOCK + threadIdx.x;
+    const size_t word = (size_t)blockIdx.x * EXT_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int s_w[32];
+    __shared__ int s_w[EXT_BLOCK / 32];
     for (int s = 0; s < K; s++) {
-        const size_t word = idx >> 5;
-        const unsigned m = (word * 32 < total) ? mask[(size_t)s * words_per_level + word] : 0u;
-        if (lane == 0) s_w[warp] = __popc(m);
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int v = s_w[threadIdx.x];
-            int incl = v;
+        unsigned m = (word * 32 < total) ? mask[(size_t)s * words_per_level + word] : 0u;
+        const int v = __popc(m);
+        int incl = v;
 #pragma unroll
-            for (int k = 1; k < 32; k <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, k);
-                if (threadIdx.x >= k) incl += t;
-            }
-            s_w[threadIdx.x] = incl - v;
+        for (int k = 1; k < 32; k <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += t;
         }
+        if (lane == 31) s_w[warp] = incl;
         __syncthreads();
-        if ((m >> lane) & 1u) {
-            const int pos = blockoff[(size_t)s * nblocks + blockIdx.x] + s_w[warp] +
-                            __popc(m & ((1u << lane) - 1u));
+        int pos = blockoff[(size_t)s * nblocks + blockIdx.x] + incl - v;
+        for (int w = 0; w < warp; w++) pos += s_w[w];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
             if (pos < cap) {
+                const size_t idx = word * 32 + bit;
                 Candidate c;
                 c.o = (short)o;
                 c.s = (short)s;
@@ -384,6 +424,7 @@ __global__ void __launch_bounds__(EXT_BLOCK)
                 c.z = (int)(r / ny) + zbase;
                 cand[pos] = c;
             }
+            pos++;
         }
         __syncthreads();
     }
@@ -448,6 +489,9 @@ int s3d_blur_fused(s3d_engine *e, const float *src, float *dst, int nx, int ny, 
                    const TapSet &taps, const float uf[3]);  // blur_fused.cu
 bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps,
                              const float uf[3]);
+int s3d_conv_dyadic_order(const TapSet &taps, float uf, int n);  // blur_dyadic.cu
+int s3d_conv_dyadic_axis(s3d_engine *e, int axis, int order, const float *src, float *dst, int nx,
+                         int ny, int nz, const TapSet &taps);
 
 int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz, int nc,
                const TapSet &taps, const float uf[3])
@@ -457,15 +501,33 @@ int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int 
     const size_t total = (size_t)nx * ny * nz * nc;
     if (s3d_ensure_scratch(e, total)) return -1;
     const int grid = grid_for(e, total, 256, 16);
-    k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0],
-                                               0, nz, 0, nz, is_dyadic(uf[0], nx));
-    S3D_LAUNCH_CHECK(e);
-    k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
-                                               taps, uf[1], 0, nz, 0, nz, is_dyadic(uf[1], ny));
-    S3D_LAUNCH_CHECK(e);
-    k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2],
-                                               0, nz, 0, nz, is_dyadic(uf[2], nz));
-    S3D_LAUNCH_CHECK(e);
+    // octaves 1 and 2 of a dyadic pyramid: register-blocked per-axis kernels (blur_dyadic.cu)
+    const int dims[3] = {nx, ny, nz};
+    int ord[3] = {-1, -1, -1};
+    if (e->blur_mode == 0 && nc == 1)
+        for (int a = 0; a < 3; a++) ord[a] = s3d_conv_dyadic_order(taps, uf[a], dims[a]);
+    if (ord[0] >= 0) {
+        if (s3d_conv_dyadic_axis(e, 0, ord[0], src, e->scratch[0], nx, ny, nz, taps)) return -1;
+    } else {
+        k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0],
+                                                   0, nz, 0, nz, is_dyadic(uf[0], nx));
+        S3D_LAUNCH_CHECK(e);
+    }
+    if (ord[1] >= 0) {
+        if (s3d_conv_dyadic_axis(e, 1, ord[1], e->scratch[0], e->scratch[1], nx, ny, nz, taps))
+            return -1;
+    } else {
+        k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
+                                                   taps, uf[1], 0, nz, 0, nz, is_dyadic(uf[1], ny));
+        S3D_LAUNCH_CHECK(e);
+    }
+    if (ord[2] >= 0) {
+        if (s3d_conv_dyadic_axis(e, 2, ord[2], e->scratch[1], dst, nx, ny, nz, taps)) return -1;
+    } else {
+        k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2],
+                                                   0, nz, 0, nz, is_dyadic(uf[2], nz));
+        S3D_LAUNCH_CHECK(e);
+    }
     return 0;
 }
 
@@ -536,8 +598,8 @@ int s3d_k_extrema_range(s3d_engine *e, int o, double peak_thresh, int zl0, int n
     const int nx = l0.g.nx, ny = l0.g.ny, nz = nzs;
     const size_t zskip = (size_t)nx * ny * zl0;
     const size_t total = (size_t)nx * ny * nz;
-    const int nblocks = (int)((total + EXT_BLOCK - 1) / EXT_BLOCK);
-    const size_t words = (size_t)nblocks * (EXT_BLOCK / 32);
+    const int nblocks = (int)((total + EXT_CHUNK - 1) / EXT_CHUNK);
+    const size_t words = (size_t)nblocks * (EXT_CHUNK / 32);
     const int K = e->K;
     if (K > EXT_MAX_LEVELS) return s3d_fail(e, "num_kp_levels too large", cudaSuccess, __FILE__, __LINE__);
     if (words * K > e->mask_cap) {
@@ -558,8 +620,12 @@ int s3d_k_extrema_range(s3d_engine *e, int o, double peak_thresh, int zl0, int n
     for (int s = -1; s <= K; s++) L.dog[s + 1] = e->dog[(size_t)o * e->nlev_d + (s + 1)].d + zskip;
     L.maxbits = e->d_scalars + 1 + (size_t)o * e->nlev_d;
     L.K = K;
-    k_extrema_mark<<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
-                                                        e->d_blockcnt, nblocks, words);
+    if (K == 3)
+        k_extrema_mark<3><<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
+                                                               e->d_blockcnt, nblocks, words);
+    else
+        k_extrema_mark<0><<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
+                                                               e->d_blockcnt, nblocks, words);
     S3D_LAUNCH_CHECK(e);
     k_extrema_scan<<<1, 1024, 0, e->stream>>>(e->d_blockcnt, nblocks, K, e->d_counter);
     S3D_LAUNCH_CHECK(e);

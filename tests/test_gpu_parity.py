@@ -148,7 +148,7 @@ def test_generic_and_fused_blur_agree_with_oracle(b200_lib, oracle_cls):
     for shape in [(37, 45, 70), (64, 64, 64), (20, 133, 31)]:
         vol = rng.random(shape, dtype=np.float32)
         for units in [(1.0, 1.0, 1.0), (2.0, 2.0, 2.0), (4.0, 4.0, 4.0), (1.0, 2.0, 0.7)]:
-            for sg in sigmas[::2] + [sigmas[-1]]:
+            for sg in sigmas:
                 taps = orc.gauss_taps(sg)
                 want = orc.blur(vol, taps, units)
                 for mode in (1, 0):

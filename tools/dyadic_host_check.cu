@@ -1,0 +1,100 @@
+// CPU check of the register-blocked dyadic FIR (sift3d_b200/csrc/blur_dyadic.cu): the same
+// __host__ __device__ line code, driven by host loops, against the oracle's apply_Sep_FIR_filter
+// restatement (oracle/sift3d_oracle.c).  TEST TOOL (loads the oracle).
+//   nvcc -O2 -I include tools/dyadic_host_check.cu oracle/_build/liboracle.so -o /tmp/dyc && /tmp/dyc
+#include "../sift3d_b200/csrc/blur_dyadic.cu"
+#include "../oracle/sift3d_oracle.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+int s3d_fail(s3d_engine *, const char *, cudaError_t, const char *, int) { return -1; }
+
+template <int AXIS, int O, int HW, int RUN>
+static void host_axis(const float *src, float *dst, int nx, int ny, int nz, const TapSet &taps)
+{
+    constexpr int P = 1 << O;
+    constexpr int UHW = (HW + P - 1) >> O;
+    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nz);
+    const int nruns = (n + RUN - 1) / RUN;
+    const size_t st = AXIS == 0 ? 1 : (AXIS == 1 ? (size_t)nx : (size_t)nx * ny);
+    const size_t nthreads = (size_t)nx * ny * nz / n * nruns;
+    const int start = UHW, end = n - 1 - (UHW + 1);
+    const float uf = 1.0f / (float)P;
+    for (size_t t = 0; t < nthreads; t++) {
+        size_t line_off;
+        int i0;
+        if (AXIS == 0) {
+            i0 = (int)(t % nruns) * RUN;
+            line_off = (t / nruns) * (size_t)nx;
+        } else if (AXIS == 1) {
+            const int x = (int)(t % nx);
+            const size_t r = t / nx;
+            i0 = (int)(r % nruns) * RUN;
+            line_off = (r / nruns) * (size_t)nx * ny + x;
+        } else {
+            const size_t plane = (size_t)nx * ny;
+            i0 = (int)(t / plane) * RUN;
+            line_off = t % plane;
+        }
+        const float *line = src + line_off;
+        float acc[RUN];
+        conv_run<O, HW, RUN>(line, st, n, i0, taps, acc);
+        if (i0 < start || i0 + RUN - 1 > end)
+            for (int k = 0; k < RUN; k++) {
+                const int i = i0 + k;
+                if (i < n && (i < start || i > end)) acc[k] = boundary_point(line, st, n, i, taps, uf);
+            }
+        float *o = dst + line_off + (size_t)i0 * st;
+        for (int k = 0; k < RUN; k++)
+            if (i0 + k < n) o[(size_t)k * st] = acc[k];
+    }
+}
+
+template <int O, int HW>
+static int check(int nx, int ny, int nz, unsigned seed)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    std::vector<float> src(n), a(n), b(n), c(n), ref(n);
+    srand(seed);
+    for (size_t i = 0; i < n; i++) src[i] = (float)rand() / (float)RAND_MAX - 0.3f;
+    TapSet taps;
+    memset(&taps, 0, sizeof(taps));
+    const double sigma = HW / 3.0 - 1e-3;
+    taps.width = orc_gauss_taps(sigma, taps.t, S3D_MAX_TAPS);
+    if (taps.width != 2 * HW + 1) { printf("width %d != %d\n", taps.width, 2 * HW + 1); return 1; }
+    const double u = (double)(1 << O);
+    const double units[3] = {u, u, u};
+    orc_blur(src.data(), ref.data(), nx, ny, nz, 1, units, taps.t, taps.width, 1.0);
+    host_axis<0, O, HW, 8>(src.data(), a.data(), nx, ny, nz, taps);
+    host_axis<1, O, HW, 16>(a.data(), b.data(), nx, ny, nz, taps);
+    host_axis<2, O, HW, 16>(b.data(), c.data(), nx, ny, nz, taps);
+    size_t bad = 0;
+    for (size_t i = 0; i < n; i++) bad += memcmp(&c[i], &ref[i], 4) != 0;
+    printf("O=%d HW=%d %dx%dx%d: %zu / %zu differ\n", O, HW, nx, ny, nz, bad, n);
+    return bad != 0;
+}
+
+int main()
+{
+    int rc = 0;
+    rc |= check<0, 2>(37, 21, 19, 21);
+    rc |= check<0, 3>(13, 21, 19, 22);
+    rc |= check<0, 8>(37, 18, 41, 23);
+    rc |= check<0, 5>(8, 8, 8, 24);
+    rc |= check<1, 3>(37, 21, 19, 1);
+    rc |= check<1, 4>(40, 33, 18, 2);
+    rc |= check<1, 5>(16, 17, 35, 3);
+    rc |= check<1, 6>(45, 16, 23, 4);
+    rc |= check<1, 8>(64, 47, 33, 5);
+    rc |= check<2, 3>(37, 21, 19, 6);
+    rc |= check<2, 4>(32, 33, 18, 7);
+    rc |= check<2, 5>(16, 17, 35, 8);
+    rc |= check<2, 6>(45, 16, 23, 9);
+    rc |= check<2, 8>(64, 47, 33, 10);
+    rc |= check<1, 8>(8, 9, 10, 11);
+    rc |= check<2, 8>(8, 9, 10, 12);
+    printf(rc ? "FAIL\n" : "all bit-identical\n");
+    return rc;
+}
