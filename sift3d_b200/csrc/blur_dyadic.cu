@@ -75,20 +75,20 @@ __host__ __device__ __noinline__ float boundary_point(const float *line, size_t 
     return acc;
 }
 
-template <int O, int HW, int RUN>
-__host__ __device__ __forceinline__ void conv_run(const float *__restrict__ line, size_t st, int n, int i0,
-                                         const TapSet &taps, float (&acc)[RUN])
+// ld(jj) returns sample i0 + jj of the line (any jj in [-UHW, RUN + OFFMAX])
+template <int O, int HW, int RUN, class Loader>
+__host__ __device__ __forceinline__ void conv_run_ld(const Loader &ld, const TapSet &taps,
+                                                     float (&acc)[RUN])
 {
     constexpr int P = 1 << O;
     constexpr int UHW = (HW + P - 1) >> O;  // ceil(HW / P): reach towards lower coordinates
     constexpr int OFFMAX = HW >> O;         // floor(HW / P): reach towards higher coordinates
 #pragma unroll
     for (int k = 0; k < RUN; k++) acc[k] = 0.0f;
-    const int last = n - 1;
-    float hi = LDG(line + (size_t)s3d_clampi(i0 + RUN + OFFMAX, last) * st);
+    float hi = ld(RUN + OFFMAX);
 #pragma unroll
     for (int jj = RUN - 1 + OFFMAX; jj >= -UHW; jj--) {  // sample j = i0 + jj
-        const float lo = LDG(line + (size_t)s3d_clampi(i0 + jj, last) * st);
+        const float lo = ld(jj);
 #pragma unroll
         for (int r = P - 1; r >= 0; r--) {
             // used by output k iff d = -((jj - k) * P + r) lies in [-HW, HW]
@@ -111,8 +111,121 @@ __host__ __device__ __forceinline__ void conv_run(const float *__restrict__ line
     }
 }
 
-// AXIS 0: thread = RUN consecutive x of one row; AXIS 1 / 2: thread = one x, RUN consecutive
-// y / z (lanes are x neighbours: every load and store of a warp is one coalesced segment).
+template <int O, int HW, int RUN>
+__host__ __device__ __forceinline__ void conv_run(const float *__restrict__ line, size_t st, int n,
+                                                  int i0, const TapSet &taps, float (&acc)[RUN])
+{
+    const int last = n - 1;
+    conv_run_ld<O, HW, RUN>(
+        [&](int jj) { return LDG(line + (size_t)s3d_clampi(i0 + jj, last) * st); }, taps, acc);
+}
+
+// ---- x axis through shared memory -------------------------------------------------------------
+// A block stages XT_ROWS rows x (XT_OUT outputs + filter reach) samples with coalesced loads,
+// every thread then owns 8 consecutive outputs of one staged row (32 threads per row), and the
+// results go back through the same buffer for coalesced stores.  One pad word per 8 samples
+// makes the lanes' strided accesses (8 words apart) conflict-free: word c lives at c + (c >> 3),
+// lane l reads 9 * l + const.  The three phases are __host__ __device__ (tools/dyadic_host_check.cu
+// runs them tid by tid); the kernel separates them with __syncthreads().
+#define XT_OUT 256
+#define XT_ROWS 8
+#define XT_RUN 8
+
+template <int O, int HW>
+struct XTile {
+    static constexpr int P = 1 << O;
+    static constexpr int UHW = (HW + P - 1) >> O;
+    static constexpr int OFFMAX = HW >> O;
+    static constexpr int W = XT_OUT + UHW + OFFMAX + 1;  // staged samples per row
+    static constexpr int WP = W + (W >> 3) + 1;           // with pad words
+};
+
+__host__ __device__ __forceinline__ int xt_phys(int c) { return c + (c >> 3); }
+
+template <int O, int HW>
+__host__ __device__ __forceinline__ void xtile_load(int tid, float *s, const float *src, int nx,
+                                                    size_t nrows, int x_base, size_t row0)
+{
+    using T = XTile<O, HW>;
+    for (int e = tid; e < XT_ROWS * T::W; e += XT_OUT) {
+        const int r = e / T::W, c = e - r * T::W;
+        const size_t row = row0 + r;
+        if (row < nrows)
+            s[r * T::WP + xt_phys(c)] = LDG(src + row * (size_t)nx + s3d_clampi(x_base - T::UHW + c, nx - 1));
+    }
+}
+
+template <int O, int HW>
+__host__ __device__ __forceinline__ void xtile_compute(int tid, const float *s, const float *src,
+                                                       int nx, size_t nrows, int x_base, size_t row0,
+                                                       const TapSet &taps, float (&acc)[XT_RUN])
+{
+    using T = XTile<O, HW>;
+    const int r = tid >> 5, l = tid & 31;
+    const size_t row = row0 + r;
+    const int i0 = x_base + XT_RUN * l;
+    if (row >= nrows || i0 >= nx) return;
+    const float *srow = s + r * T::WP;
+    const int c0 = XT_RUN * l + T::UHW;  // staged index of sample i0
+    conv_run_ld<O, HW, XT_RUN>([&](int jj) { return srow[xt_phys(c0 + jj)]; }, taps, acc);
+    const int start = T::UHW, end = nx - 1 - (T::UHW + 1);
+    if (i0 < start || i0 + XT_RUN - 1 > end) {
+        const float *line = src + row * (size_t)nx;
+#pragma unroll
+        for (int k = 0; k < XT_RUN; k++) {
+            const int i = i0 + k;
+            if (i < nx && (i < start || i > end))
+                acc[k] = boundary_point(line, 1, nx, i, taps, 1.0f / (float)T::P);
+        }
+    }
+}
+
+template <int O, int HW>
+__host__ __device__ __forceinline__ void xtile_stage(int tid, float *s, const float (&acc)[XT_RUN])
+{
+    using T = XTile<O, HW>;
+    const int r = tid >> 5, l = tid & 31;
+#pragma unroll
+    for (int k = 0; k < XT_RUN; k++) s[r * T::WP + xt_phys(XT_RUN * l + k)] = acc[k];
+}
+
+template <int O, int HW>
+__host__ __device__ __forceinline__ void xtile_store(int tid, const float *s, float *dst, int nx,
+                                                     size_t nrows, int x_base, size_t row0)
+{
+    using T = XTile<O, HW>;
+    for (int e = tid; e < XT_ROWS * XT_OUT; e += XT_OUT) {
+        const int r = e / XT_OUT, c = e - r * XT_OUT;
+        const size_t row = row0 + r;
+        if (row < nrows && x_base + c < nx) dst[row * (size_t)nx + x_base + c] = s[r * T::WP + xt_phys(c)];
+    }
+}
+
+template <int O, int HW>
+__global__ void __launch_bounds__(XT_OUT) k_conv_dyadic_x(const float *__restrict__ src,
+                                                          float *__restrict__ dst, int nx,
+                                                          size_t nrows, int ntx,
+                                                          const __grid_constant__ TapSet taps)
+{
+    using T = XTile<O, HW>;
+    __shared__ float s[XT_ROWS * T::WP];
+    const int x_base = (int)(blockIdx.x % ntx) * XT_OUT;
+    const size_t row0 = (size_t)(blockIdx.x / ntx) * XT_ROWS;
+    xtile_load<O, HW>(threadIdx.x, s, src, nx, nrows, x_base, row0);
+    __syncthreads();
+    float acc[XT_RUN];
+#pragma unroll
+    for (int k = 0; k < XT_RUN; k++) acc[k] = 0.0f;
+    xtile_compute<O, HW>(threadIdx.x, s, src, nx, nrows, x_base, row0, taps, acc);
+    __syncthreads();
+    xtile_stage<O, HW>(threadIdx.x, s, acc);
+    __syncthreads();
+    xtile_store<O, HW>(threadIdx.x, s, dst, nx, nrows, x_base, row0);
+}
+
+// y / z axes (AXIS 1 / 2): thread = one x, RUN consecutive y / z; lanes are x neighbours, so every
+// load and store of a warp is one coalesced segment.  (AXIS 0 also works -- thread = RUN
+// consecutive x -- but its strided accesses are slow: the x axis uses k_conv_dyadic_x.)
 template <int AXIS, int O, int HW, int RUN>
 __global__ void __launch_bounds__(256) k_conv_dyadic(const float *__restrict__ src,
                                                      float *__restrict__ dst, int nx, int ny,
@@ -165,14 +278,23 @@ template <int AXIS, int O, int HW>
 int launch_one(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
                const TapSet &taps)
 {
-    constexpr int RUN = AXIS == 0 ? 8 : 16;
-    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nz);
+    if (AXIS == 0) {
+        const size_t nrows = (size_t)ny * nz;
+        const int ntx = (nx + XT_OUT - 1) / XT_OUT;
+        const size_t nblocks = (size_t)ntx * ((nrows + XT_ROWS - 1) / XT_ROWS);
+        if (nblocks > 0x7fffffffull) return 1;
+        k_conv_dyadic_x<O, HW><<<(unsigned)nblocks, XT_OUT, 0, e->stream>>>(src, dst, nx, nrows, ntx, taps);
+        S3D_LAUNCH_CHECK(e);
+        return 0;
+    }
+    constexpr int RUN = 16;
+    const int n = AXIS == 1 ? ny : nz;
     const size_t nruns = (size_t)(n + RUN - 1) / RUN;
     const size_t nthreads = (size_t)nx * ny * nz / (size_t)n * nruns;
     const size_t want = (nthreads + 255) / 256;
     const size_t cap = (size_t)e->num_sms * 64;
     const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-    k_conv_dyadic<AXIS, O, HW, RUN><<<grid, 256, 0, e->stream>>>(src, dst, nx, ny, nz, taps);
+    k_conv_dyadic<(AXIS == 0 ? 1 : AXIS), O, HW, RUN><<<grid, 256, 0, e->stream>>>(src, dst, nx, ny, nz, taps);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
@@ -188,6 +310,9 @@ int launch_hw(s3d_engine *e, const float *src, float *dst, int nx, int ny, int n
     case 5: return launch_one<AXIS, O, 5>(e, src, dst, nx, ny, nz, taps);
     case 6: return launch_one<AXIS, O, 6>(e, src, dst, nx, ny, nz, taps);
     case 8: return launch_one<AXIS, O, 8>(e, src, dst, nx, ny, nz, taps);
+    case 7: if (O == 0) return launch_one<AXIS, 0, 7>(e, src, dst, nx, ny, nz, taps); return 1;
+    case 9: if (O == 0) return launch_one<AXIS, 0, 9>(e, src, dst, nx, ny, nz, taps); return 1;
+    case 10: if (O == 0) return launch_one<AXIS, 0, 10>(e, src, dst, nx, ny, nz, taps); return 1;
     default: return 1;
     }
 }
@@ -200,15 +325,17 @@ int launch_hw(s3d_engine *e, const float *src, float *dst, int nx, int ny, int n
 int s3d_conv_dyadic_order(const TapSet &taps, float uf, int n)
 {
     const int hw = taps.width / 2;
-    if (!(hw == 2 || hw == 3 || hw == 4 || hw == 5 || hw == 6 || hw == 8)) return -1;
+    const bool pyr = hw == 2 || hw == 3 || hw == 4 || hw == 5 || hw == 6 || hw == 8;
     if ((long long)n >= (1ll << 20)) return -1;
-    if (uf == 1.0f) return 0;
+    if (uf == 1.0f && (pyr || hw == 7 || hw == 9 || hw == 10)) return 0;  // + dense window widths
+    if (!pyr) return -1;
     if (uf == 0.5f) return 1;
     if (uf == 0.25f) return 2;
     return -1;
 }
 
-// one axis of the separable filter; returns 1 if (axis, order, width) is not instantiated
+// one axis of the separable filter; returns 1 if (axis, order, width) is not instantiated,
+// -1 on a launch error
 int s3d_conv_dyadic_axis(s3d_engine *e, int axis, int order, const float *src, float *dst, int nx,
                          int ny, int nz, const TapSet &taps)
 {

@@ -74,6 +74,7 @@ struct s3d_engine {
     int blur_mode = 0;
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
+    int opt_desc_occ = 4;   // CTAs per SM k_descriptor2 is compiled for (3 or 4)
     int opt_desc_path = 0;  // test hook: force a fixed-point path of k_descriptor2 (0 = automatic)
     double blur_w[4] = {1.05, 1.10, 1.05, 1.10};  // per-plane cost of edge columns (left,right,top,bottom)
     int opt_blur_flags = 0;  // timing experiments only (results wrong when non-zero)
@@ -122,6 +123,14 @@ struct s3d_engine {
     size_t ori_pool_cap = 0;
     void *d_ori_tabs = nullptr;
     size_t ori_tabs_cap = 0;
+
+    // dense-descriptor buffers (raw, smoothed, 12-channel temp, 12-channel result), kept between
+    // calls, and the pinned staging ring of the pageable-destination download
+    float *dense_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t dense_cap[4] = {0, 0, 0, 0};
+    void *stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+    int opt_dense_copy = 1;  // 1 = staged parallel download, 0 = plain cudaMemcpy into pageable memory
 
     // descriptor scratch
     s3d_keypoint *d_kp_in = nullptr;

@@ -5,6 +5,9 @@
 // design and the reference-compatible structs; everything per-voxel happens here.
 #include "common.cuh"
 
+#include <thread>
+#include <ctime>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -160,6 +163,10 @@ int s3d_engine_create(s3d_engine **out, int device)
         return -1;
     }
     e->stream = e->own_stream;
+    // tuning / A-B switches for the tools (same as s3d_set_option)
+    if (const char *v = getenv("S3D_BLUR_MODE")) e->blur_mode = atoi(v);
+    if (const char *v = getenv("S3D_DENSE_COPY")) e->opt_dense_copy = atoi(v);
+    if (const char *v = getenv("S3D_DESC_OCC")) e->opt_desc_occ = atoi(v);
     if ((ce = cudaMalloc(&e->d_counter, 4 * sizeof(int))) != cudaSuccess) {
         s3d_fail(nullptr, "cudaMalloc", ce, __FILE__, __LINE__);
         cudaStreamDestroy(e->own_stream);
@@ -183,6 +190,10 @@ void s3d_engine_destroy(s3d_engine *e)
         if (p) cudaFree(p);
     for (auto &t : e->segtabs)
         if (t.d) cudaFree(t.d);
+    for (float *p : e->dense_buf)
+        if (p) cudaFree(p);
+    for (void *p : e->stage)
+        if (p) cudaFreeHost(p);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -221,6 +232,8 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "desc_v1")) e->opt_desc_v1 = value;
     else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 3;
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
+    else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
+    else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
     else if (!strcmp(name, "blur_dbg")) {
         DeviceGuard guard(e->device);
         if (value && !e->d_blur_dbg) {
@@ -663,6 +676,82 @@ int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx,
     return s3d_k_blur(e, dev_src, dev_dst, nx, ny, nz, nc, t, uf);
 }
 
+// wall-clock trace of the dense path (S3D_TRACE=1)
+static double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+static int dense_ensure(s3d_engine *e, int i, size_t bytes)
+{
+    if (bytes <= e->dense_cap[i]) return 0;
+    if (e->dense_buf[i]) cudaFree(e->dense_buf[i]);
+    e->dense_buf[i] = nullptr;
+    e->dense_cap[i] = 0;
+    S3D_CUDA(e, cudaMalloc(&e->dense_buf[i], bytes));
+    e->dense_cap[i] = bytes;
+    return 0;
+}
+
+// Device -> PAGEABLE host memory (the caller's malloc'ed Image, SURVEY.md 8b ownership rule).
+// A plain cudaMemcpy stages through the driver's bounce buffer and copies out on one core; here
+// the DMA lands in a ring of two pinned buffers and a team of host threads copies each chunk
+// out (and takes the first-touch page faults of a fresh allocation in parallel) while the DMA
+// fills the other buffer.
+static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
+{
+    const size_t CH = (size_t)32 << 20;
+    if (!e->opt_dense_copy || bytes < 2 * CH) {
+        S3D_CUDA(e, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, e->stream));
+        S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+        return 0;
+    }
+    if (e->stage_cap < CH) {
+        for (int i = 0; i < 2; i++) {
+            if (e->stage[i]) cudaFreeHost(e->stage[i]);
+            e->stage[i] = nullptr;
+        }
+        e->stage_cap = 0;
+        for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaHostAlloc(&e->stage[i], CH, cudaHostAllocDefault));
+        e->stage_cap = CH;
+    }
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    const size_t nch = (bytes + CH - 1) / CH;
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = nthr < 1 ? 1 : (nthr > 8 ? 8 : nthr);
+    cudaError_t ce = cudaSuccess;
+    auto issue = [&](size_t c) {
+        const size_t off = c * CH, len = std::min(CH, bytes - off);
+        ce = cudaMemcpyAsync(e->stage[c & 1], (const char *)dev + off, len, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[c & 1], e->stream);
+    };
+    issue(0);
+    for (size_t c = 0; c < nch && ce == cudaSuccess; c++) {
+        ce = cudaEventSynchronize(ev[c & 1]);
+        if (ce != cudaSuccess) break;
+        if (c + 1 < nch) issue(c + 1);  // the other buffer: free since chunk c-1 was copied out
+        const size_t off = c * CH, len = std::min(CH, bytes - off);
+        const char *src = (const char *)e->stage[c & 1];
+        char *d = (char *)dst + off;
+        std::vector<std::thread> team;
+        const size_t part = ((len + nthr - 1) / nthr + 4095) & ~(size_t)4095;
+        for (unsigned t = 1; t < nthr; t++) {
+            const size_t lo = t * part;
+            if (lo >= len) break;
+            team.emplace_back([=] { memcpy(d + lo, src + lo, std::min(part, len - lo)); });
+        }
+        memcpy(d, src, std::min(part, len));
+        for (auto &th : team) th.join();
+    }
+    cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    if (ce != cudaSuccess) return s3d_fail(e, "staged download", ce, __FILE__, __LINE__);
+    return 0;
+}
+
 int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, int nz, size_t xs,
                           size_t ys, size_t zs, const double units[3],
                           const double desc_units[3], const s3d_filter *smooth,
@@ -672,15 +761,18 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
     const size_t n = (size_t)nx * ny * nz;
     TapSet ts, tw;
     if (to_tapset(e, smooth, ts) || to_tapset(e, window, tw)) return -1;
-    float *raw = nullptr, *sm = nullptr, *t12 = nullptr, *d12 = nullptr;
+    const bool trace = getenv("S3D_TRACE") != nullptr;
+    double t[8];
+    t[0] = now_ms();
+    if (dense_ensure(e, 0, n * 4) || dense_ensure(e, 1, n * 4) || dense_ensure(e, 2, n * 48) ||
+        dense_ensure(e, 3, n * 48))
+        return -1;
+    float *raw = e->dense_buf[0], *sm = e->dense_buf[1], *t12 = e->dense_buf[2], *d12 = e->dense_buf[3];
     int rc = -1;
     do {
-        if (cudaMalloc(&raw, n * 4) != cudaSuccess || cudaMalloc(&sm, n * 4) != cudaSuccess ||
-            cudaMalloc(&t12, n * 48) != cudaSuccess || cudaMalloc(&d12, n * 48) != cudaSuccess) {
-            s3d_fail(e, "dense: cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
-            break;
-        }
         if (upload_strided(e, raw, host_in, nx, ny, nz, xs, ys, zs)) break;
+        if (trace) cudaStreamSynchronize(e->stream);
+        t[1] = now_ms();
         // smooth_scale_raw_input (sift.c:1978-2006)
         const float uf[3] = {(float)(1.0 / units[0]), (float)(1.0 / units[1]), (float)(1.0 / units[2])};
         if (s3d_k_blur(e, raw, sm, nx, ny, nz, 1, ts, uf)) break;
@@ -691,24 +783,26 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
         const float fu[3] = {(float)units[0], (float)units[1], (float)units[2]};
         const float iu[3] = {1.0f / fu[0], 1.0f / fu[1], 1.0f / fu[2]};
         if (s3d_k_dense(e, sm, raw, nx, ny, nz, iu, t12)) break;
+        if (trace) cudaStreamSynchronize(e->stream);
+        t[2] = now_ms();
         // 12-channel window blur in the units of the caller's desc image (sift.c:2451, 2483)
         const float ufd[3] = {(float)(1.0 / desc_units[0]), (float)(1.0 / desc_units[1]),
                               (float)(1.0 / desc_units[2])};
         if (s3d_k_blur(e, t12, d12, nx, ny, nz, 12, tw, ufd)) break;
+        if (trace) cudaStreamSynchronize(e->stream);
+        t[3] = now_ms();
         if (s3d_k_dense_post(e, d12, raw, n)) break;
-        cudaError_t ce = cudaMemcpyAsync(host_out, d12, n * 48, cudaMemcpyDeviceToHost, e->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-        if (ce != cudaSuccess) {
-            s3d_fail(e, "dense: download", ce, __FILE__, __LINE__);
-            break;
-        }
+        if (trace) cudaStreamSynchronize(e->stream);
+        t[4] = now_ms();
+        if (d2h_pageable(e, host_out, d12, n * 48)) break;
+        t[5] = now_ms();
         rc = 0;
     } while (0);
     cudaStreamSynchronize(e->stream);
-    if (raw) cudaFree(raw);
-    if (sm) cudaFree(sm);
-    if (t12) cudaFree(t12);
-    if (d12) cudaFree(d12);
+    if (trace && rc == 0)
+        fprintf(stderr, "[s3d dense %dx%dx%d] alloc %.2f upload %.2f smooth+bary %.2f blur12 %.2f post %.2f "
+                        "download %.2f ms\n", nx, ny, nz, 0.0, t[1] - t[0], t[2] - t[1], t[3] - t[2],
+                t[4] - t[3], t[5] - t[4]);
     return rc;
 }
 

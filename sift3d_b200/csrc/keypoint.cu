@@ -36,20 +36,63 @@ __constant__ float c_vmid[20][3];
 // vertices (+-1,+-1,+-1), (+-1/phi,0,+-phi), (+-phi,+-1/phi,0), (0,+-phi,+-1/phi) of a dodecahedron
 __constant__ int c_face_lut[32];
 
+// Where the per-face constants and the preselection table live.  FaceMem: plain pointers (any
+// kernel).  FaceSh: byte addresses in the shared window -- k_descriptor2 keeps ONE opaque base
+// register for all of its shared data, because nvcc otherwise rematerialises the window base
+// (S2R SR_CgaCtaId + MOV + LEA) at every access site under the register cap.
+// Word k of a FaceConst: e1 0-2, e2 3-5, t 6-8, q 9-11, e2q 12, idx 13-15.
+struct FaceMem {
+    const FaceConst *F;
+    const int *L;
+    template <int K>
+    __device__ __forceinline__ float w(int face) const
+    {
+        return reinterpret_cast<const float *>(F + face)[K];
+    }
+    template <int K>
+    __device__ __forceinline__ int idx(int face) const { return F[face].idx[K]; }
+    __device__ __forceinline__ int lut(int i) const { return L[i]; }
+};
+struct FaceSh {
+    unsigned fa, la;  // shared-window byte addresses of FaceConst[20] and of the lut
+    template <int K>
+    __device__ __forceinline__ float w(int face) const
+    {
+        float v;
+        asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(fa + (unsigned)face * (unsigned)sizeof(FaceConst)), "n"(4 * K));
+        return v;
+    }
+    template <int K>
+    __device__ __forceinline__ int idx(int face) const
+    {
+        int v;
+        asm("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(fa + (unsigned)face * (unsigned)sizeof(FaceConst)), "n"(4 * (13 + K)));
+        return v;
+    }
+    __device__ __forceinline__ int lut(int i) const
+    {
+        int v;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(la + 4u * (unsigned)i));
+        return v;
+    }
+};
+
 // cart2bary (sift.c:335-394) with the per-face constants hoisted.
-__device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], float bary[3])
+template <class FA>
+__device__ __forceinline__ bool face_test(const FA &F, int f, const float g[3], float bary[3])
 {
+    const float e20 = F.template w<3>(f), e21 = F.template w<4>(f), e22 = F.template w<5>(f);
     float p[3];
-    p[0] = fs(fm(g[1], F.e2[2]), fm(g[2], F.e2[1]));
-    p[1] = fs(fm(g[2], F.e2[0]), fm(g[0], F.e2[2]));
-    p[2] = fs(fm(g[0], F.e2[1]), fm(g[1], F.e2[0]));
-    const float det = dot3(F.e1[0], p[0], F.e1[1], p[1], F.e1[2], p[2]);
+    p[0] = fs(fm(g[1], e22), fm(g[2], e21));
+    p[1] = fs(fm(g[2], e20), fm(g[0], e22));
+    p[2] = fs(fm(g[0], e21), fm(g[1], e20));
+    const float det = dot3(F.template w<0>(f), p[0], F.template w<1>(f), p[1], F.template w<2>(f), p[2]);
     if ((double)fabsf(det) < K_BARY_EPS) return false;
     const float det_inv = __fdiv_rn(1.0f, det);
-    bary[1] = fm(det_inv, dot3(F.t[0], p[0], F.t[1], p[1], F.t[2], p[2]));
-    bary[2] = fm(det_inv, dot3(g[0], F.q[0], g[1], F.q[1], g[2], F.q[2]));
+    bary[1] = fm(det_inv, dot3(F.template w<6>(f), p[0], F.template w<7>(f), p[1], F.template w<8>(f), p[2]));
+    bary[2] = fm(det_inv, dot3(g[0], F.template w<9>(f), g[1], F.template w<10>(f), g[2], F.template w<11>(f)));
     bary[0] = fs(fs(1.0f, bary[1]), bary[2]);
-    const float k = fm(F.e2q, det_inv);
+    const float k = fm(F.template w<12>(f), det_inv);
     return !((double)bary[0] < -K_BARY_EPS || (double)bary[1] < -K_BARY_EPS ||
              (double)bary[2] < -K_BARY_EPS || k < 0.0f);
 }
@@ -59,8 +102,9 @@ __device__ __forceinline__ bool face_test(const FaceConst &F, const float g[3], 
 // is the containing face; if its barycentrics are all comfortably positive no
 // other face can pass (faces only overlap within bary_eps of shared edges), so
 // it is also the first.  Otherwise fall back to the literal in-order loop.
-__device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, const int *lut,
-                                        const float g[3], float bary[3], const bool fast = true)
+template <class FA>
+__device__ __forceinline__ int icos_bin_t(const FA &F, const float g[3], float bary[3],
+                                          const bool fast = true)
 {
     const float n2 = fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2]));
     if ((double)n2 < K_BARY_EPS) return -1;
@@ -79,15 +123,22 @@ __device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, 
         if (s2 > bs) bs = s2, type = 2;
         if (s3 > bs) bs = s3, type = 3;
         const int sb = (g[0] < 0.0f ? 1 : 0) | (g[1] < 0.0f ? 2 : 0) | (g[2] < 0.0f ? 4 : 0);
-        const int best = lut[type * 8 + sb];
+        const int best = F.lut(type * 8 + sb);
         const float margin = 1e-4f;
-        if (face_test(F[best], g, bary) && bary[0] > margin && bary[1] > margin &&
+        if (face_test(F, best, g, bary) && bary[0] > margin && bary[1] > margin &&
             bary[2] > margin)
             return best;
     }
     for (int i = 0; i < 20; i++)
-        if (face_test(F[i], g, bary)) return i;
+        if (face_test(F, i, g, bary)) return i;
     return -1;
+}
+
+__device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, const int *lut,
+                                        const float g[3], float bary[3], const bool fast = true)
+{
+    const FaceMem A{F, lut};
+    return icos_bin_t(A, g, bary, fast);
 }
 
 // stage the per-face constants in shared memory (divergent indexing by face)
@@ -217,7 +268,23 @@ __constant__ unsigned long long c_exp2f_tab[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
 
-__device__ __forceinline__ float expf_glibc(float x, const unsigned long long *tab /* shared */)
+// TabPtr / TabSh: the 32-entry table through a pointer or a shared-window byte address
+struct TabPtr {
+    const unsigned long long *t;
+    __device__ __forceinline__ unsigned long long operator()(unsigned i) const { return t[i]; }
+};
+struct TabSh {
+    unsigned a;
+    __device__ __forceinline__ unsigned long long operator()(unsigned i) const
+    {
+        unsigned long long v;
+        asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a + 8u * i));
+        return v;
+    }
+};
+
+template <class TAB>
+__device__ __forceinline__ float expf_glibc_t(float x, const TAB &tab)
 {
     const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
     const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32,
@@ -227,7 +294,7 @@ __device__ __forceinline__ float expf_glibc(float x, const unsigned long long *t
     const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
     kd = __dsub_rn(kd, SHIFT);
     const double r = __dsub_rn(z, kd);
-    const unsigned long long t = tab[ki & 31] + (ki << 47);
+    const unsigned long long t = tab((unsigned)ki & 31u) + (ki << 47);
     const double sc = __longlong_as_double((long long)t);
     const double zz = __fma_rn(C0, r, C1);
     const double r2 = __dmul_rn(r, r);
@@ -235,6 +302,11 @@ __device__ __forceinline__ float expf_glibc(float x, const unsigned long long *t
     y = __fma_rn(zz, r2, y);
     y = __dmul_rn(y, sc);
     return (float)y;
+}
+
+__device__ __forceinline__ float expf_glibc(float x, const unsigned long long *tab /* shared */)
+{
+    return expf_glibc_t(x, TabPtr{tab});
 }
 
 // Second half of assign_eig_ori (sift.c:1424-1497): eigenvectors of the structure tensor,
@@ -735,6 +807,35 @@ __device__ __forceinline__ void atoms_inc(unsigned addr)
 {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
+__device__ __forceinline__ float ld_shared_f32(unsigned addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// ... with a compile-time byte offset folded into the address operand
+template <int OFF>
+__device__ __forceinline__ unsigned atoms_add_off(unsigned addr, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1+%3], %2;" : "=r"(old) : "r"(addr), "r"(v), "n"(OFF) : "memory");
+    return old;
+}
+template <int OFF>
+__device__ __forceinline__ void atoms_inc_off(unsigned addr)
+{
+    asm volatile("red.shared.add.u32 [%0+%1], 1;" ::"r"(addr), "n"(OFF) : "memory");
+}
+
+// shared-memory image of k_descriptor2 (one struct = one base register, see FaceSh)
+#define D2_HSTRIDE (12 * 125 + 4)
+struct D2Smem {
+    int h_fx[2 * D2_HSTRIDE];  // lo words, then hi words, of the fixed-point histogram (5x5x5 cells)
+    unsigned long long tab[32];
+    FaceConst face[20];
+    int lut[32];
+    float kc[2];  // r2, s2
+};
 
 // Descriptor, version 2 (the default).  One CTA (8 warps) per keypoint; every warp owns every
 // 8th row of the window's bounding box, 32 rows per chunk:
@@ -764,24 +865,43 @@ __device__ __forceinline__ void atoms_inc(unsigned addr)
 #define FX_CARRY 1
 #endif
 
-__global__ void __launch_bounds__(DESC2_THREADS, 4)
+// OCC: resident CTAs per SM the register budget is compiled for (4: 64 registers, the
+// per-voxel geometry is partly rematerialised; 3: 80 registers).  HOOK: the test hook that
+// forces one of the fixed-point paths is compiled in (production instantiation: false).
+template <int OCC, bool HOOK>
+__global__ void __launch_bounds__(DESC2_THREADS, OCC)
     k_descriptor2(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
     __shared__ int4 s_rows[DESC2_THREADS / 32][33];  // per warp: {first index, xa, y, z} of 32 rows
     __shared__ float hist[S3D_DESC_NUMEL];
     // lo and hi words of the fixed-point histogram in ONE array, so that both atomics of an
-    // update share an address register; +48: dummy slots for out-of-grid corners (lane + vertex)
-    constexpr int HSTRIDE = S3D_DESC_NUMEL + 48;
-    __shared__ int h_fx[2 * HSTRIDE];
+    // update share an address register.  The 4x4x4 grid of cells is stored as 5x5x5: a trilinear
+    // corner that steps out of the grid (base index 3, step up) lands in a padding cell that is
+    // never read back, so the scatter needs no bounds logic and every corner is the base cell's
+    // address plus a COMPILE-TIME offset (folded into the ATOMS address operand).
+    constexpr int HSTRIDE = D2_HSTRIDE;
+    // Everything the per-voxel code touches sits in ONE struct addressed from one opaque base
+    // register `sb` (see FaceSh): histogram words, expf table, face constants, lut, constants.
+    __shared__ D2Smem S;
+    int *const h_fx = S.h_fx;
     unsigned *h_lo = reinterpret_cast<unsigned *>(h_fx);
     int *h_hi = h_fx + HSTRIDE;
-    const unsigned h_addr = (unsigned)__cvta_generic_to_shared(h_fx);
-    __shared__ unsigned long long s_tab[32];
+    unsigned sb = (unsigned)__cvta_generic_to_shared(&S);
+    asm volatile("" : "+r"(sb));  // opaque: keeps the compiler from rematerialising it
+    const unsigned h_addr = sb + (unsigned)offsetof(D2Smem, h_fx);
+    unsigned long long *const s_tab = S.tab;
+    FaceConst *const s_face = S.face;
+    int *const s_lut = S.lut;
+    float *const s_kc = S.kc;
+    const FaceSh faces{sb + (unsigned)offsetof(D2Smem, face), sb + (unsigned)offsetof(D2Smem, lut)};
+    const TabSh etab{sb + (unsigned)offsetof(D2Smem, tab)};
+    const unsigned kc_addr = sb + (unsigned)offsetof(D2Smem, kc);
     __shared__ double s_red[DESC2_THREADS / 32];
-    __shared__ FaceConst s_face[20];
-    __shared__ int s_lut[32];
     __shared__ float s_norm_inv;
+    // S.kc: block constants the per-voxel code reads back with an opaque load: r2 and s2 derive
+    // from kp.sd through f64 arithmetic, and under the register cap the compiler otherwise
+    // REMATERIALISES that chain (2 DMUL + 3 F2F) for every voxel
     const int ki = blockIdx.x;
     if (ki >= n) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -830,10 +950,11 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
     }
     // test hook (s3d_set_option "desc_path"): 1 = signed general path, 2 = large-contribution
     // path, 3 = legacy 2^-32 / 64-bit carry path -- all must agree with the default
-    const int force_path = icos_fast >> 1;
+    const int force_path = HOOK ? icos_fast >> 1 : 0;
     icos_fast &= 1;
     if (force_path == 3) split = false;
     if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
+    if (tid == 0) s_kc[0] = r2, s_kc[1] = s2;
     load_faces(s_face, s_lut, M);
     __syncthreads();
 
@@ -936,6 +1057,24 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
         int4 cur = rows[r];
         int row_end = rows[r + 1].x;
         int x = cur.y + (idx - cur.x);
+        // Row constants (y and z are fixed along a row): the y/z terms of the squared distance
+        // and of the three rotated coordinates -- the SAME products the per-voxel expression
+        // forms, only formed once per row -- and the row's base offset.
+        float py, pz, ry[3], rz[3];
+        size_t rowoff;
+        auto set_row = [&](const int4 &c) {
+            const float vy = fm(fs((float)c.z, kp.y), uyf);
+            const float vz = fm(fs((float)c.w, kp.z), uzf);
+            py = fm(vy, vy);
+            pz = fm(vz, vz);
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                ry[a] = fm(Rt[3 * a + 1], vy);
+                rz[a] = fm(Rt[3 * a + 2], vz);
+            }
+            rowoff = (size_t)c.z * ys + (size_t)c.w * zs;
+        };
+        set_row(cur);
         for (int k = 0; k < L; k++, idx++, x++) {
             if (idx >= idx_end) break;
             while (idx >= row_end) {  // next non-empty row
@@ -943,11 +1082,22 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                 cur = rows[r];
                 row_end = rows[r + 1].x;
                 x = cur.y;
+                set_row(cur);
             }
-            const int y = cur.z, z = cur.w;
-            float sq, vb[3];
-            if (!geom(x, y, z, sq, vb)) continue;
-            const size_t voff = x + (size_t)y * ys + (size_t)z * zs;
+            // geom(x, y, z) with the row terms hoisted
+            const float vx = fm(fs((float)x, kp.x), uxf);
+            const float sq = fa(fa(fm(vx, vx), py), pz);
+            if (sq > ld_shared_f32(kc_addr)) continue;  // r2
+            float vb[3];
+            bool inside = true;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float vk = fa(fa(fm(Rt[3 * a], vx), ry[a]), rz[a]);
+                vb[a] = fm(fa(vk, half), bin_fctr);
+                inside = inside && !(vb[a] < 0.0f || vb[a] >= 4.0f);
+            }
+            if (!inside) continue;
+            const size_t voff = rowoff + x;
             float g[3];
             if (gim) {  // block-uniform: one 16-byte gather instead of six 4-byte ones
                 const float4 g4 = __ldg(gim + voff);
@@ -959,7 +1109,8 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                 g[2] = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
             }
             // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument
-            const float wgt_win = expf_glibc(__fdiv_rn(fm(-0.5f, sq), s2), s_tab);
+            const float wgt_win =
+                expf_glibc_t(__fdiv_rn(fm(-0.5f, sq), ld_shared_f32(kc_addr + 4u)), etab);  // / s2
             g[0] = fm(g[0], wgt_win);
             g[1] = fm(g[1], wgt_win);
             g[2] = fm(g[2], wgt_win);
@@ -968,7 +1119,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
             for (int a = 0; a < 3; a++)
                 gr[a] = dot3(Rt[3 * a], g[0], Rt[3 * a + 1], g[1], Rt[3 * a + 2], g[2]);
             float bary[3];
-            const int bin = icos_bin(s_face, s_lut, gr, bary, icos_fast != 0);
+            const int bin = icos_bin_t(faces, gr, bary, icos_fast != 0);
             if (bin < 0) continue;
             const float mag =
                 __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
@@ -979,7 +1130,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
                 dv[a] = fs(vb[a], floorf(vb[a]));
                 ib[a] = (int)vb[a];
             }
-            const int i0 = s_face[bin].idx[0], i1 = s_face[bin].idx[1], i2 = s_face[bin].idx[2];
+            const int i0 = faces.idx<0>(bin), i1 = faces.idx<1>(bin), i2 = faces.idx<2>(bin);
             // mag * 2^S: scaling by a power of two commutes with every rounding below, so
             // fm(fm(mag_s, wgt), bary) == fm(fm(mag, wgt), bary) * 2^S (sift.c:1763-1765)
             const float mag_s = fm(mag, split ? fx_scale : 4294967296.0f);
@@ -988,47 +1139,54 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
             // the reference: (x * y) * z
             const float wx0 = fs(1.0f, dv[0]), wy0 = fs(1.0f, dv[1]), wz0 = fs(1.0f, dv[2]);
             const float wxy[4] = {fm(wx0, wy0), fm(wx0, dv[1]), fm(dv[0], wy0), fm(dv[0], dv[1])};
-            // corners outside the 4x4x4 grid add nothing: they are steered to per-lane dummy
-            // slots so that the scatter stays branch-free.  ib <= 3, so a corner is outside iff
-            // it steps up along an axis whose base index is already 3.
-            const bool ex = ib[0] == 3, ey = ib[1] == 3, ez = ib[2] == 3;
-            int *const base_in = h_fx + 12 * (ib[0] + 4 * ib[1] + 16 * ib[2]);
-            int *const base_out = h_fx + S3D_DESC_NUMEL + lane;
+            const int cbase = 12 * (ib[0] + 5 * ib[1] + 25 * ib[2]);  // base cell, padded layout
             const bool fast = split && small && FX_CARRY && force_path == 0 && bary[0] >= 0.0f &&
                               bary[1] >= 0.0f && bary[2] >= 0.0f;
-            // shared-window byte addresses of the three vertex bins of the base cell, and the
-            // offset that moves them into this lane's dummy slots
-            const unsigned va0 = h_addr + 4u * (unsigned)(12 * (ib[0] + 4 * ib[1] + 16 * ib[2]) + i0);
-            const unsigned va1 = va0 + 4u * (unsigned)(i1 - i0), va2 = va0 + 4u * (unsigned)(i2 - i0);
-            const unsigned dummy_off =
-                4u * (unsigned)(S3D_DESC_NUMEL + lane - 12 * (ib[0] + 4 * ib[1] + 16 * ib[2]));
-#pragma unroll
+            if (fast) {
+                // Non-negative contributions (all but gradients within bary_eps outside an
+                // edge): lo word += q with ONE ATOMS whose returned old value gives the carry
+                // (q > ~old); hi word += 1 only then.  The three updates of a corner are issued
+                // together so that their round trips overlap.
+                const unsigned va0 = h_addr + 4u * (unsigned)(cbase + i0);
+                const unsigned va1 = h_addr + 4u * (unsigned)(cbase + i1);
+                const unsigned va2 = h_addr + 4u * (unsigned)(cbase + i2);
+#define S3D_CORNER(DX, DY, DZ)                                                                \
+    {                                                                                         \
+        constexpr int COFF = 48 * ((DX) + 5 * (DY) + 25 * (DZ));                              \
+        const float mw = fm(mag_s, fm(wxy[2 * (DX) + (DY)], (DZ) ? dv[2] : wz0));             \
+        const unsigned q0 = __float2uint_rn(fm(mw, bary[0])),                                 \
+                       q1 = __float2uint_rn(fm(mw, bary[1])),                                 \
+                       q2 = __float2uint_rn(fm(mw, bary[2]));                                 \
+        const unsigned o0 = atoms_add_off<COFF>(va0, q0), o1 = atoms_add_off<COFF>(va1, q1),  \
+                       o2 = atoms_add_off<COFF>(va2, q2);                                     \
+        const bool c0 = q0 > ~o0, c1 = q1 > ~o1, c2 = q2 > ~o2;                               \
+        if (c0 | c1 | c2) {                                                                   \
+            if (c0) atoms_inc_off<COFF + 4 * HSTRIDE>(va0);                                   \
+            if (c1) atoms_inc_off<COFF + 4 * HSTRIDE>(va1);                                   \
+            if (c2) atoms_inc_off<COFF + 4 * HSTRIDE>(va2);                                   \
+        }                                                                                     \
+    }
+                S3D_CORNER(0, 0, 0)
+                S3D_CORNER(0, 0, 1)
+                S3D_CORNER(0, 1, 0)
+                S3D_CORNER(0, 1, 1)
+                S3D_CORNER(1, 0, 0)
+                S3D_CORNER(1, 0, 1)
+                S3D_CORNER(1, 1, 0)
+                S3D_CORNER(1, 1, 1)
+#undef S3D_CORNER
+                continue;
+            }
+            // rare paths (a negative barycentric weight, huge contributions, test hook): one
+            // compact loop over the corners, corner indices at run time
+#pragma unroll 1
             for (int c = 0; c < 8; c++) {
                 const int dx = c >> 2, dy = (c >> 1) & 1, dz = c & 1;
-                const bool in = !((dx && ex) || (dy && ey) || (dz && ez));
-                int *const cell = in ? base_in + 12 * (dx + 4 * dy + 16 * dz) : base_out;
-                const float wgt = fm(wxy[2 * dx + dy], dz ? dv[2] : wz0);
+                int *const cell = h_fx + cbase + 12 * (dx + 5 * dy + 25 * dz);
+                // same products as wxy[] above (no dynamically indexed array: no stack frame)
+                const float wgt = fm(fm(dx ? dv[0] : wx0, dy ? dv[1] : wy0), dz ? dv[2] : wz0);
                 const float mw = fm(mag_s, wgt);
-                if (fast) {
-                    // non-negative contributions (all but gradients within bary_eps outside an
-                    // edge): lo word += q with ONE ATOMS whose returned old value gives the
-                    // carry (q > ~old); hi word += 1 only then.  The three updates of a corner
-                    // are issued together so that their round trips overlap.  32-bit shared
-                    // addresses: one IADD per update (vertex address + corner offset).
-                    const unsigned coff = in ? 48u * (dx + 4 * dy + 16 * dz) : dummy_off;
-                    const unsigned a0 = va0 + coff, a1 = va1 + coff, a2 = va2 + coff;
-                    const unsigned q0 = __float2uint_rn(fm(mw, bary[0])),
-                                   q1 = __float2uint_rn(fm(mw, bary[1])),
-                                   q2 = __float2uint_rn(fm(mw, bary[2]));
-                    const unsigned o0 = atoms_add(a0, q0), o1 = atoms_add(a1, q1),
-                                   o2 = atoms_add(a2, q2);
-                    const bool c0 = q0 > ~o0, c1 = q1 > ~o1, c2 = q2 > ~o2;
-                    if (c0 | c1 | c2) {
-                        if (c0) atoms_inc(a0 + 4u * HSTRIDE);
-                        if (c1) atoms_inc(a1 + 4u * HSTRIDE);
-                        if (c2) atoms_inc(a2 + 4u * HSTRIDE);
-                    }
-                } else if (split && small) {
+                if (split && small) {
                     if (FX_CARRY) {  // signed: hi += sign(q) + carry
                         int q[3], qh[3];
                         unsigned old[3];
@@ -1044,11 +1202,9 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
 #pragma unroll
                         for (int j = 0; j < 3; j++)
                             qh[j] = (q[j] >> 31) + ((old[j] + (unsigned)q[j]) < old[j] ? 1 : 0);
-                        if (qh[0] | qh[1] | qh[2]) {
 #pragma unroll
-                            for (int j = 0; j < 3; j++)
-                                if (qh[j]) atomicAdd(bp[j] + HSTRIDE, qh[j]);
-                        }
+                        for (int j = 0; j < 3; j++)
+                            if (qh[j]) atomicAdd(bp[j] + HSTRIDE, qh[j]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 3; j++) {
@@ -1092,13 +1248,15 @@ __global__ void __launch_bounds__(DESC2_THREADS, 4)
     }
     __syncthreads();
 
-    // fixed point -> f32
+    // fixed point -> f32 (interior cells of the padded layout)
     for (int i = tid; i < S3D_DESC_NUMEL; i += DESC2_THREADS) {
+        const int cellv = i / 12, v12 = i - 12 * cellv;
+        const int p = 12 * ((cellv & 3) + 5 * ((cellv >> 2) & 3) + 25 * (cellv >> 4)) + v12;
         if (split && !FX_CARRY) {
-            const long long v = (long long)h_hi[i] * 65536ll + (long long)(int)h_lo[i];
+            const long long v = (long long)h_hi[p] * 65536ll + (long long)(int)h_lo[p];
             hist[i] = (float)((double)v * (1.0 / (double)fx_scale));
         } else {
-            const long long v = ((long long)h_hi[i] << 32) + (long long)h_lo[i];
+            const long long v = ((long long)h_hi[p] << 32) + (long long)h_lo[p];
             hist[i] = (float)((double)v * (1.0 / (split ? (double)fx_scale : 4294967296.0)));
         }
     }
@@ -1593,9 +1751,15 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
     if (e->opt_desc_v1)
         k_descriptor<<<n, DESC_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
                                                         e->opt_icos_fast);
+    else if (e->opt_desc_path)
+        k_descriptor2<4, true><<<n, DESC2_THREADS, 0, e->stream>>>(
+            d_kp, n, T, e->d_mesh, d_out, (e->opt_icos_fast & 1) | (e->opt_desc_path << 1));
+    else if (e->opt_desc_occ == 3)
+        k_descriptor2<3, false><<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
+                                                                   e->opt_icos_fast & 1);
     else
-        k_descriptor2<<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
-                                                          (e->opt_icos_fast & 1) | (e->opt_desc_path << 1));
+        k_descriptor2<4, false><<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
+                                                                   e->opt_icos_fast & 1);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }

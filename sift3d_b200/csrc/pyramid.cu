@@ -501,29 +501,38 @@ int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int 
     const size_t total = (size_t)nx * ny * nz * nc;
     if (s3d_ensure_scratch(e, total)) return -1;
     const int grid = grid_for(e, total, 256, 16);
-    // octaves 1 and 2 of a dyadic pyramid: register-blocked per-axis kernels (blur_dyadic.cu)
+    // dyadic tap spacings (octaves 0-2 of a pyramid with power-of-two units, the 12-channel dense
+    // window blur): register-blocked per-axis kernels (blur_dyadic.cu).  Interleaved channels are
+    // a reinterpretation of the same layout: along x the array is [ny*nz rows][nx][nc] -- a "y"
+    // pass over lines of stride nc -- and along y / z a row is nx*nc contiguous floats.
     const int dims[3] = {nx, ny, nz};
     int ord[3] = {-1, -1, -1};
-    if (e->blur_mode == 0 && nc == 1)
+    if (e->blur_mode == 0 && (size_t)ny * nz < 0x7fffffffull && (size_t)nx * nc < 0x7fffffffull)
         for (int a = 0; a < 3; a++) ord[a] = s3d_conv_dyadic_order(taps, uf[a], dims[a]);
-    if (ord[0] >= 0) {
-        if (s3d_conv_dyadic_axis(e, 0, ord[0], src, e->scratch[0], nx, ny, nz, taps)) return -1;
-    } else {
+    int rc = 1;
+    if (ord[0] >= 0)
+        rc = nc == 1 ? s3d_conv_dyadic_axis(e, 0, ord[0], src, e->scratch[0], nx, ny, nz, taps)
+                     : s3d_conv_dyadic_axis(e, 1, ord[0], src, e->scratch[0], nc, nx, ny * nz, taps);
+    if (rc < 0) return -1;
+    if (rc) {
         k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src, e->scratch[0], nx, ny, nz, nc, taps, uf[0],
                                                    0, nz, 0, nz, is_dyadic(uf[0], nx));
         S3D_LAUNCH_CHECK(e);
     }
-    if (ord[1] >= 0) {
-        if (s3d_conv_dyadic_axis(e, 1, ord[1], e->scratch[0], e->scratch[1], nx, ny, nz, taps))
-            return -1;
-    } else {
+    rc = 1;
+    if (ord[1] >= 0)
+        rc = s3d_conv_dyadic_axis(e, 1, ord[1], e->scratch[0], e->scratch[1], nx * nc, ny, nz, taps);
+    if (rc < 0) return -1;
+    if (rc) {
         k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, nz, nc,
                                                    taps, uf[1], 0, nz, 0, nz, is_dyadic(uf[1], ny));
         S3D_LAUNCH_CHECK(e);
     }
-    if (ord[2] >= 0) {
-        if (s3d_conv_dyadic_axis(e, 2, ord[2], e->scratch[1], dst, nx, ny, nz, taps)) return -1;
-    } else {
+    rc = 1;
+    if (ord[2] >= 0)
+        rc = s3d_conv_dyadic_axis(e, 2, ord[2], e->scratch[1], dst, nx * nc, ny, nz, taps);
+    if (rc < 0) return -1;
+    if (rc) {
         k_conv_axis<2><<<grid, 256, 0, e->stream>>>(e->scratch[1], dst, nx, ny, nz, nc, taps, uf[2],
                                                    0, nz, 0, nz, is_dyadic(uf[2], nz));
         S3D_LAUNCH_CHECK(e);
