@@ -168,15 +168,30 @@ __host__ __device__ __forceinline__ void xtile_compute(int tid, const float *s, 
     const float *srow = s + r * T::WP;
     const int c0 = XT_RUN * l + T::UHW;  // staged index of sample i0
     conv_run_ld<O, HW, XT_RUN>([&](int jj) { return srow[xt_phys(c0 + jj)]; }, taps, acc);
+}
+
+// Outputs outside the reference's interior range [uhw, nx-2-uhw] (a handful at either end of a
+// row) take the literal mirror path.  The 32 lanes that own a staged row share them, one output
+// per lane: left to their owners they would serialise 8 outputs x all taps in the first and the
+// last lane of EVERY warp while the other 30 lanes wait.
+template <int O, int HW>
+__host__ __device__ __forceinline__ void xtile_fix_ends(int tid, float *s, const float *src, int nx,
+                                                        size_t nrows, int x_base, size_t row0,
+                                                        const TapSet &taps)
+{
+    using T = XTile<O, HW>;
+    const int r = tid >> 5, l = tid & 31;
+    const size_t row = row0 + r;
+    if (row >= nrows) return;
     const int start = T::UHW, end = nx - 1 - (T::UHW + 1);
-    if (i0 < start || i0 + XT_RUN - 1 > end) {
-        const float *line = src + row * (size_t)nx;
-#pragma unroll
-        for (int k = 0; k < XT_RUN; k++) {
-            const int i = i0 + k;
-            if (i < nx && (i < start || i > end))
-                acc[k] = boundary_point(line, 1, nx, i, taps, 1.0f / (float)T::P);
-        }
+    const int nl = start < nx ? start : nx;                  // outputs [0, nl)
+    const int rb = end + 1 > nl ? end + 1 : nl;               // outputs [rb, nx)
+    const int nb = nl + (nx - rb);
+    const float *line = src + row * (size_t)nx;
+    for (int b = l; b < nb; b += 32) {
+        const int i = b < nl ? b : rb + (b - nl);
+        if (i >= x_base && i < x_base + XT_OUT)
+            s[r * T::WP + xt_phys(i - x_base)] = boundary_point(line, 1, nx, i, taps, 1.0f / (float)T::P);
     }
 }
 
@@ -220,6 +235,10 @@ __global__ void __launch_bounds__(XT_OUT) k_conv_dyadic_x(const float *__restric
     __syncthreads();
     xtile_stage<O, HW>(threadIdx.x, s, acc);
     __syncthreads();
+    if (x_base < T::UHW || x_base + XT_OUT > nx - 1 - (T::UHW + 1)) {  // tile touches a row end
+        xtile_fix_ends<O, HW>(threadIdx.x, s, src, nx, nrows, x_base, row0, taps);
+        __syncthreads();
+    }
     xtile_store<O, HW>(threadIdx.x, s, dst, nx, nrows, x_base, row0);
 }
 

@@ -813,6 +813,13 @@ __device__ __forceinline__ float ld_shared_f32(unsigned addr)
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+// mask = 2 * mask + carry_out(old + q): the carry flag travels inside ONE asm statement
+__device__ __forceinline__ void carry_push(unsigned &mask, unsigned old, unsigned q)
+{
+    unsigned sum;
+    asm("{\n\tadd.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %1, %1;\n\t}" : "=r"(sum), "+r"(mask) : "r"(old), "r"(q));
+    (void)sum;
+}
 // ... with a compile-time byte offset folded into the address operand
 template <int OFF>
 __device__ __forceinline__ unsigned atoms_add_off(unsigned addr, unsigned v)
@@ -1159,13 +1166,14 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
                        q2 = __float2uint_rn(fm(mw, bary[2]));                                 \
         const unsigned o0 = atoms_add_off<COFF>(va0, q0), o1 = atoms_add_off<COFF>(va1, q1),  \
                        o2 = atoms_add_off<COFF>(va2, q2);                                     \
-        const bool c0 = q0 > ~o0, c1 = q1 > ~o1, c2 = q2 > ~o2;                               \
-        if (c0 | c1 | c2) {                                                                   \
-            if (c0) atoms_inc_off<COFF + 4 * HSTRIDE>(va0);                                   \
-            if (c1) atoms_inc_off<COFF + 4 * HSTRIDE>(va1);                                   \
-            if (c2) atoms_inc_off<COFF + 4 * HSTRIDE>(va2);                                   \
-        }                                                                                     \
+        carry_push(cmask, o0, q0);                                                            \
+        carry_push(cmask, o1, q1);                                                            \
+        carry_push(cmask, o2, q2);                                                            \
     }
+                // cmask collects the carry-out of old + q of the 24 updates (first update =
+                // bit 23): two instructions per update (IADD3 with carry-out, IADD3.X), and ONE
+                // test per voxel instead of a compare/branch per corner
+                unsigned cmask = 0;
                 S3D_CORNER(0, 0, 0)
                 S3D_CORNER(0, 0, 1)
                 S3D_CORNER(0, 1, 0)
@@ -1174,6 +1182,14 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
                 S3D_CORNER(1, 0, 1)
                 S3D_CORNER(1, 1, 0)
                 S3D_CORNER(1, 1, 1)
+                while (cmask) {  // rare: hi word += 1 for every update that wrapped its lo word
+                    const int b = 31 - __clz(cmask);
+                    cmask &= ~(1u << b);
+                    const int u = 23 - b, c = u / 3, j = u - 3 * c;
+                    const unsigned va = j == 0 ? va0 : (j == 1 ? va1 : va2);
+                    atoms_inc(va + 4u * HSTRIDE +
+                              48u * (unsigned)((c >> 2) + 5 * ((c >> 1) & 1) + 25 * (c & 1)));
+                }
 #undef S3D_CORNER
                 continue;
             }

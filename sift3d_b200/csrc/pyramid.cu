@@ -273,7 +273,7 @@ __device__ __forceinline__ bool ext_test(const ExtLevels &L, int s, size_t idx, 
 }
 
 template <int KT>  // KT > 0: K == KT known at compile time; KT == 0: any K <= EXT_MAX_LEVELS
-__global__ void __launch_bounds__(EXT_BLOCK)
+__global__ void __launch_bounds__(EXT_BLOCK, KT > 0 ? 4 : 1)
     k_extrema_mark(const ExtLevels L, int nx, int ny, int nz, double peak_thresh,
                    unsigned *__restrict__ mask, int *__restrict__ blockcnt, int nblocks,
                    size_t words_per_level)

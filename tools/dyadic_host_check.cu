@@ -76,6 +76,7 @@ static void host_xtile(const float *src, float *dst, int nx, int ny, int nz, con
             memcpy(acc, &accs[tid * XT_RUN], sizeof(acc));
             xtile_stage<O, HW>(tid, s.data(), acc);
         }
+        for (int tid = 0; tid < XT_OUT; tid++) xtile_fix_ends<O, HW>(tid, s.data(), src, nx, nrows, x_base, row0, taps);
         for (int tid = 0; tid < XT_OUT; tid++) xtile_store<O, HW>(tid, s.data(), dst, nx, nrows, x_base, row0);
     }
 }

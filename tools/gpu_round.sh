@@ -1,24 +1,18 @@
 #!/usr/bin/env bash
-# One GPU visit: parity tests, bench line, descriptor-kernel variants (S3D_DESC_OCC) under ncu.
+# One GPU visit: parity tests, bench line, launch list, descriptor kernel ncu capture.
 # usage: tools/gpu_round.sh <tag>
 tag=${1:-x}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $out/pytest_gpu.txt
-S3D_DESC_OCC=3 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -5 > $out/pytest_gpu_occ3.txt
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_occ4.json 2> $out/bench_occ4.err
-S3D_DESC_OCC=3 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_occ3.json 2> $out/bench_occ3.err
-for occ in 4 3; do
-S3D_DESC_OCC=$occ timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed \
-    --clock-control none -k regex:k_descriptor2 -s 1 -c 1 python tools/run_desc.py 192 > $out/ncu_desc_occ$occ.txt 2>&1
-done
-tail -3 $out/pytest_gpu.txt $out/pytest_gpu_occ3.txt
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n1.json 2> $out/bench_n1.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file $out/launches.csv \
+    python bench.py --steps 1 --warmup 2 --no-cpu-baseline --blur-reps 1 > $out/bench_under_ncu.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_descriptor2 -s 1 -c 1 -o $out/desc \
+    python tools/run_desc.py 192 > $out/ncu_desc.log 2>&1
+tail -n 3 $out/pytest_gpu.txt
 python - <<PY
 import json
-for occ in (4,3):
-    try:
-        d=json.loads(open("$out/bench_occ%d.json"%occ).read().strip().splitlines()[-1])
-        print("occ",occ,d["ms_per_step"],d["e2e"]["ms_per_step"],d["stages_ms"])
-    except Exception as ex: print("occ",occ,"failed",ex)
+d=json.loads(open("$out/bench_n1.json").read().strip().splitlines()[-1])
+print(d["ms_per_step"],d["e2e"]["ms_per_step"],d["stages_ms"])
 PY
-grep -E "gpu__time|inst_executed|issue_active|lsu_wave" $out/ncu_desc_occ4.txt $out/ncu_desc_occ3.txt
