@@ -260,20 +260,8 @@ struct ExtLevels {
     int K;
 };
 
-__device__ __forceinline__ bool ext_test(const ExtLevels &L, int s, size_t idx, float v, float thr,
-                                         size_t ys, size_t zs)
-{
-    if (!(v > thr || v < -thr)) return false;
-    const float *cur = L.dog[s + 1] + idx;
-    const float p = __ldg(L.dog[s] + idx), q = __ldg(L.dog[s + 2] + idx);
-    const float a0 = __ldg(cur + 1), a1 = __ldg(cur - 1), a2 = __ldg(cur + ys), a3 = __ldg(cur - ys),
-                a4 = __ldg(cur - zs), a5 = __ldg(cur + zs);
-    return (v > p && v > a0 && v > a1 && v > a2 && v > a3 && v > a4 && v > a5 && v > q) ||
-           (v < p && v < a0 && v < a1 && v < a2 && v < a3 && v < a4 && v < a5 && v < q);
-}
-
 template <int KT>  // KT > 0: K == KT known at compile time; KT == 0: any K <= EXT_MAX_LEVELS
-__global__ void __launch_bounds__(EXT_BLOCK, KT > 0 ? 4 : 1)
+__global__ void __launch_bounds__(EXT_BLOCK, KT > 0 ? 3 : 1)
     k_extrema_mark(const ExtLevels L, int nx, int ny, int nz, double peak_thresh,
                    unsigned *__restrict__ mask, int *__restrict__ blockcnt, int nblocks,
                    size_t words_per_level)
@@ -324,11 +312,35 @@ __global__ void __launch_bounds__(EXT_BLOCK, KT > 0 ? 4 : 1)
 #pragma unroll
         for (int u = 0; u < EXT_UNROLL; u++) {
             if (base + (size_t)(it + u) * EXT_BLOCK >= total) break;  // block-uniform
+            // The eight neighbours of every level that passes the threshold are fetched with
+            // PREDICATED loads issued back to back (one latency for all levels of the voxel,
+            // not one dependent branch per level); compares and ballots follow.
+            float nb[KA][8];
+            bool need[KA];
+#pragma unroll
+            for (int s = 0; s < KA; s++) {
+                need[s] = s < K && interior[u] && (v[u][s] > thr[s] || v[u][s] < -thr[s]);
+                const float *cur = L.dog[s < K ? s + 1 : 1] + idx[u];
+                nb[s][0] = need[s] ? __ldg(L.dog[s < K ? s : 0] + idx[u]) : 0.0f;
+                nb[s][1] = need[s] ? __ldg(L.dog[s < K ? s + 2 : 2] + idx[u]) : 0.0f;
+                nb[s][2] = need[s] ? __ldg(cur + 1) : 0.0f;
+                nb[s][3] = need[s] ? __ldg(cur - 1) : 0.0f;
+                nb[s][4] = need[s] ? __ldg(cur + ys) : 0.0f;
+                nb[s][5] = need[s] ? __ldg(cur - ys) : 0.0f;
+                nb[s][6] = need[s] ? __ldg(cur - zs) : 0.0f;
+                nb[s][7] = need[s] ? __ldg(cur + zs) : 0.0f;
+            }
 #pragma unroll
             for (int s = 0; s < KA; s++) {
                 if (s >= K) break;
-                const bool hit = interior[u] && ext_test(L, s, idx[u], v[u][s], thr[s], ys, zs);
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                const float c = v[u][s];
+                bool mx = need[s], mn = need[s];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    mx = mx && c > nb[s][j];
+                    mn = mn && c < nb[s][j];
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, mx || mn);
                 if ((threadIdx.x & 31) == 0) {
                     mask[(size_t)s * words_per_level + (idx[u] >> 5)] = m;
                     cnt[s] += __popc(m);
