@@ -341,11 +341,20 @@ static int ensure_im(s3d_engine *e, int nx, int ny, int nz)
     return 0;
 }
 
+static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes);
+
 static int upload_strided(s3d_engine *e, float *dev, const float *host, int nx, int ny, int nz,
                           size_t xs, size_t ys, size_t zs)
 {
     const size_t n = (size_t)nx * ny * nz;
     if (xs == 1 && ys == (size_t)nx && zs == (size_t)nx * ny) {
+        // the caller's Image is usually malloc memory (pageable): staged parallel upload;
+        // pinned / registered memory goes straight to the DMA engine
+        cudaPointerAttributes at;
+        const bool pageable = cudaPointerGetAttributes(&at, host) != cudaSuccess ||
+                              at.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable) return h2d_pageable(e, dev, host, n * sizeof(float));
         S3D_CUDA(e, cudaMemcpyAsync(dev, host, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         return 0;
     }
@@ -695,6 +704,35 @@ static int dense_ensure(s3d_engine *e, int i, size_t bytes)
     return 0;
 }
 
+static int stage_ensure(s3d_engine *e, size_t bytes)
+{
+    if (e->stage_cap >= bytes) return 0;
+    for (int i = 0; i < 2; i++) {
+        if (e->stage[i]) cudaFreeHost(e->stage[i]);
+        e->stage[i] = nullptr;
+    }
+    e->stage_cap = 0;
+    for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaHostAlloc(&e->stage[i], bytes, cudaHostAllocDefault));
+    e->stage_cap = bytes;
+    return 0;
+}
+
+// memcpy by a team of up to 8 host threads (page-aligned shares)
+static void par_memcpy(char *d, const char *src, size_t len)
+{
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = nthr < 1 ? 1 : (nthr > 8 ? 8 : nthr);
+    const size_t part = ((len + nthr - 1) / nthr + 4095) & ~(size_t)4095;
+    std::vector<std::thread> team;
+    for (unsigned t = 1; t < nthr; t++) {
+        const size_t lo = t * part;
+        if (lo >= len) break;
+        team.emplace_back([=] { memcpy(d + lo, src + lo, std::min(part, len - lo)); });
+    }
+    memcpy(d, src, std::min(part, len));
+    for (auto &th : team) th.join();
+}
+
 // Device -> PAGEABLE host memory (the caller's malloc'ed Image, SURVEY.md 8b ownership rule).
 // A plain cudaMemcpy stages through the driver's bounce buffer and copies out on one core; here
 // the DMA lands in a ring of two pinned buffers and a team of host threads copies each chunk
@@ -708,20 +746,10 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));
         return 0;
     }
-    if (e->stage_cap < CH) {
-        for (int i = 0; i < 2; i++) {
-            if (e->stage[i]) cudaFreeHost(e->stage[i]);
-            e->stage[i] = nullptr;
-        }
-        e->stage_cap = 0;
-        for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaHostAlloc(&e->stage[i], CH, cudaHostAllocDefault));
-        e->stage_cap = CH;
-    }
+    if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     const size_t nch = (bytes + CH - 1) / CH;
-    unsigned nthr = std::thread::hardware_concurrency();
-    nthr = nthr < 1 ? 1 : (nthr > 8 ? 8 : nthr);
     cudaError_t ce = cudaSuccess;
     auto issue = [&](size_t c) {
         const size_t off = c * CH, len = std::min(CH, bytes - off);
@@ -734,21 +762,39 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
         if (ce != cudaSuccess) break;
         if (c + 1 < nch) issue(c + 1);  // the other buffer: free since chunk c-1 was copied out
         const size_t off = c * CH, len = std::min(CH, bytes - off);
-        const char *src = (const char *)e->stage[c & 1];
-        char *d = (char *)dst + off;
-        std::vector<std::thread> team;
-        const size_t part = ((len + nthr - 1) / nthr + 4095) & ~(size_t)4095;
-        for (unsigned t = 1; t < nthr; t++) {
-            const size_t lo = t * part;
-            if (lo >= len) break;
-            team.emplace_back([=] { memcpy(d + lo, src + lo, std::min(part, len - lo)); });
-        }
-        memcpy(d, src, std::min(part, len));
-        for (auto &th : team) th.join();
+        par_memcpy((char *)dst + off, (const char *)e->stage[c & 1], len);
     }
     cudaStreamSynchronize(e->stream);
     for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
     if (ce != cudaSuccess) return s3d_fail(e, "staged download", ce, __FILE__, __LINE__);
+    return 0;
+}
+
+// PAGEABLE host memory -> device, the mirror image: a team of host threads fills one pinned
+// buffer while the DMA drains the other.
+static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes)
+{
+    const size_t CH = (size_t)32 << 20;
+    if (!e->opt_dense_copy || bytes < 2 * CH) {
+        S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
+        return 0;
+    }
+    if (stage_ensure(e, CH)) return -1;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    const size_t nch = (bytes + CH - 1) / CH;
+    cudaError_t ce = cudaStreamSynchronize(e->stream);  // earlier users of the staging ring
+    for (size_t c = 0; c < nch && ce == cudaSuccess; c++) {
+        if (c >= 2) ce = cudaEventSynchronize(ev[c & 1]);  // its previous DMA has drained
+        if (ce != cudaSuccess) break;
+        const size_t off = c * CH, len = std::min(CH, bytes - off);
+        par_memcpy((char *)e->stage[c & 1], (const char *)host + off, len);
+        ce = cudaMemcpyAsync((char *)dev + off, e->stage[c & 1], len, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[c & 1], e->stream);
+    }
+    cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ev[i]);
+    if (ce != cudaSuccess) return s3d_fail(e, "staged upload", ce, __FILE__, __LINE__);
     return 0;
 }
 
@@ -815,14 +861,10 @@ int s3d_dense_descriptors_rotate(s3d_engine *e, const float *host_in, int nx, in
     const size_t n = (size_t)nx * ny * nz;
     TapSet ts;
     if (to_tapset(e, smooth, ts)) return -1;
-    float *raw = nullptr, *sm = nullptr, *d12 = nullptr;
+    if (dense_ensure(e, 0, n * 4) || dense_ensure(e, 1, n * 4) || dense_ensure(e, 3, n * 48)) return -1;
+    float *raw = e->dense_buf[0], *sm = e->dense_buf[1], *d12 = e->dense_buf[3];
     int rc = -1;
     do {
-        if (cudaMalloc(&raw, n * 4) != cudaSuccess || cudaMalloc(&sm, n * 4) != cudaSuccess ||
-            cudaMalloc(&d12, n * 48) != cudaSuccess) {
-            s3d_fail(e, "dense rotate: cudaMalloc", cudaGetLastError(), __FILE__, __LINE__);
-            break;
-        }
         if (upload_strided(e, raw, host_in, nx, ny, nz, xs, ys, zs)) break;
         // smooth_scale_raw_input (sift.c:1978-2006)
         const float uf[3] = {(float)(1.0 / units[0]), (float)(1.0 / units[1]), (float)(1.0 / units[2])};
@@ -835,18 +877,10 @@ int s3d_dense_descriptors_rotate(s3d_engine *e, const float *host_in, int nx, in
         if (s3d_k_dense_rotate(e, sm, nx, ny, nz, fu, ori_sigma, desc_sigma, corner_thresh, d12))
             break;
         if (s3d_k_dense_post(e, d12, raw, n)) break;
-        cudaError_t ce = cudaMemcpyAsync(host_out, d12, n * 48, cudaMemcpyDeviceToHost, e->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-        if (ce != cudaSuccess) {
-            s3d_fail(e, "dense rotate: download", ce, __FILE__, __LINE__);
-            break;
-        }
+        if (d2h_pageable(e, host_out, d12, n * 48)) break;
         rc = 0;
     } while (0);
     cudaStreamSynchronize(e->stream);
-    if (raw) cudaFree(raw);
-    if (sm) cudaFree(sm);
-    if (d12) cudaFree(d12);
     return rc;
 }
 

@@ -15,4 +15,8 @@ with capi.Sift3D(lib) as s:
     assert lib.lib.SIFT3D_extract_raw_descriptors(C.byref(s.s), C.byref(im), C.byref(s.kp), C.byref(s.desc)) == 0
     conf = C.POINTER(C.c_double)()
     assert lib.lib.SIFT3D_assign_orientations(C.byref(s.s), C.byref(im), C.byref(s.kp), C.byref(conf)) == 0
-print("ok", len(kp), d.shape, dd.shape)
+    # row length not a multiple of 4: octave 0 takes the register-blocked per-axis kernels
+    vol2 = blob_volume((30, 33, 70), seed=5)
+    kp2 = s.detect_keypoints(vol2)
+    d2 = s.extract_descriptors() if len(kp2) else None
+print("ok", len(kp), d.shape, dd.shape, len(kp2))
