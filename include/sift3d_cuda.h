@@ -208,7 +208,9 @@ int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx,
 /* 0 = auto (fused fast path when eligible), 1 = force the generic per-axis path. */
 int s3d_set_blur_mode(s3d_engine *e, int mode);
 /* Debug/tuning switches: "icos_fast" (1), "blur_mode" (0), "desc_v1" (0), "desc_path" (0: automatic;
- * 1..3 force one of the descriptor kernel's fixed-point fallback paths -- tests only). */
+ * 1..3 force one of the descriptor kernel's fixed-point fallback paths, +4 leaves its row intervals
+ * untrimmed -- tests only), "desc_occ" (4: CTAs per SM the descriptor kernel is compiled for; 3),
+ * "dense_copy" (1: staged parallel copies to/from pageable host memory). */
 int s3d_set_option(s3d_engine *e, const char *name, int value);
 /* Debug: per-CTA {start, end clock, SM id, steps} of the last fused blur (after option "blur_dbg"). */
 int s3d_debug_read(s3d_engine *e, void *host, size_t bytes);

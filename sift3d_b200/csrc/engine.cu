@@ -230,7 +230,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     if (!strcmp(name, "icos_fast")) e->opt_icos_fast = value;
     else if (!strcmp(name, "blur_mode")) e->blur_mode = value;
     else if (!strcmp(name, "desc_v1")) e->opt_desc_v1 = value;
-    else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 3;
+    else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 7;
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
     else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;

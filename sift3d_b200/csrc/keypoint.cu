@@ -881,6 +881,10 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out, int icos_fast)
 {
     __shared__ int4 s_rows[DESC2_THREADS / 32][33];  // per warp: {first index, xa, y, z} of 32 rows
+    // per warp and row: the row constants of phase B -- {py, pz, ry[0..2], rz[0..2], rowoff lo/hi}
+    // -- formed in phase A by the row's own lane (all lanes busy) instead of by the one lane
+    // that crosses into the row in phase B while the other 31 wait
+    __shared__ float4 s_rowc[DESC2_THREADS / 32][32][3];
     __shared__ float hist[S3D_DESC_NUMEL];
     // lo and hi words of the fixed-point histogram in ONE array, so that both atomics of an
     // update share an address register.  The 4x4x4 grid of cells is stored as 5x5x5: a trilinear
@@ -957,7 +961,8 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
     }
     // test hook (s3d_set_option "desc_path"): 1 = signed general path, 2 = large-contribution
     // path, 3 = legacy 2^-32 / 64-bit carry path -- all must agree with the default
-    const int force_path = HOOK ? icos_fast >> 1 : 0;
+    const int force_path = HOOK ? (icos_fast >> 1) & 3 : 0;
+    const bool trim = !(HOOK && (icos_fast & 8));  // test hook: leave the row intervals untrimmed
     icos_fast &= 1;
     if (force_path == 3) split = false;
     if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
@@ -1041,6 +1046,39 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
                 }
             }
         }
+        // Row constants (the SAME products the per-voxel expression forms, once per row), and
+        // the interval TRIMMED with the exact tests: every test is weakly monotone in x under
+        // IEEE rounding, so the voxels that pass form one interval and stepping inwards from
+        // either end to the first voxel that passes yields exactly that interval.  Phase B then
+        // rejects nothing on geometry (lanes stay converged); the widening above only has to
+        // guarantee a superset.
+        if (cnt > 0) {
+            const float evy = fm(fs((float)yy, kp.y), uyf), evz = fm(fs((float)zz, kp.z), uzf);
+            const float py = fm(evy, evy), pz = fm(evz, evz);
+            const float ry0 = fm(Rt[1], evy), ry1 = fm(Rt[4], evy), ry2 = fm(Rt[7], evy);
+            const float rz0 = fm(Rt[2], evz), rz1 = fm(Rt[5], evz), rz2 = fm(Rt[8], evz);
+            auto pass = [&](int x) -> bool {
+                const float vx = fm(fs((float)x, kp.x), uxf);
+                if (fa(fa(fm(vx, vx), py), pz) > r2) return false;
+                const float b0 = fm(fa(fa(fa(fm(Rt[0], vx), ry0), rz0), half), bin_fctr);
+                const float b1 = fm(fa(fa(fa(fm(Rt[3], vx), ry1), rz1), half), bin_fctr);
+                const float b2 = fm(fa(fa(fa(fm(Rt[6], vx), ry2), rz2), half), bin_fctr);
+                return !(b0 < 0.0f || b0 >= 4.0f) && !(b1 < 0.0f || b1 >= 4.0f) &&
+                       !(b2 < 0.0f || b2 >= 4.0f);
+            };
+            if (trim) {
+                int xb = xa + cnt - 1;
+                while (xa <= xb && !pass(xa)) xa++;
+                while (xb > xa && !pass(xb)) xb--;
+                cnt = max(xb - xa + 1, 0);
+            }
+            const size_t ro = (size_t)yy * ys + (size_t)zz * zs;
+            float4 *rw = s_rowc[warp][lane];
+            rw[0] = make_float4(py, pz, ry0, ry1);
+            rw[1] = make_float4(ry2, rz0, rz1, rz2);
+            rw[2] = make_float4(__uint_as_float((unsigned)ro), __uint_as_float((unsigned)(ro >> 32)),
+                                0.0f, 0.0f);
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1069,27 +1107,25 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
         // forms, only formed once per row -- and the row's base offset.
         float py, pz, ry[3], rz[3];
         size_t rowoff;
-        auto set_row = [&](const int4 &c) {
-            const float vy = fm(fs((float)c.z, kp.y), uyf);
-            const float vz = fm(fs((float)c.w, kp.z), uzf);
-            py = fm(vy, vy);
-            pz = fm(vz, vz);
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                ry[a] = fm(Rt[3 * a + 1], vy);
-                rz[a] = fm(Rt[3 * a + 2], vz);
-            }
-            rowoff = (size_t)c.z * ys + (size_t)c.w * zs;
+        auto set_row = [&](int ri) {
+            const float4 *rc = s_rowc[warp][ri];
+            const float4 c0 = rc[0], c1 = rc[1], c2 = rc[2];
+            py = c0.x, pz = c0.y;
+            ry[0] = c0.z, ry[1] = c0.w, ry[2] = c1.x;
+            rz[0] = c1.y, rz[1] = c1.z, rz[2] = c1.w;
+            rowoff = (size_t)__float_as_uint(c2.x) | ((size_t)__float_as_uint(c2.y) << 32);
         };
-        set_row(cur);
+        if (idx < idx_end) set_row(r);
         for (int k = 0; k < L; k++, idx++, x++) {
             if (idx >= idx_end) break;
-            while (idx >= row_end) {  // next non-empty row
-                r++;
+            if (idx >= row_end) {  // next non-empty row
+                do {
+                    r++;
+                    row_end = rows[r + 1].x;
+                } while (idx >= row_end);
                 cur = rows[r];
-                row_end = rows[r + 1].x;
                 x = cur.y;
-                set_row(cur);
+                set_row(r);
             }
             // geom(x, y, z) with the row terms hoisted
             const float vx = fm(fs((float)x, kp.x), uxf);

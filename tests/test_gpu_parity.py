@@ -297,12 +297,30 @@ def test_descriptor_fixed_point_paths_agree(b200_lib):
         eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
         base = s.extract_descriptors()["hists"].copy()
         try:
-            for path in (1, 2, 3):
+            # 4 = untrimmed row intervals (phase B rejects the extra voxels itself), 5 = both:
+            # integer accumulation is order-independent, so the same visited set gives the
+            # same bits -- this pins the phase-A interval trimming
+            for path in (1, 2, 3, 4, 5):
                 assert cu.s3d_set_option(eng, b"desc_path", path) == 0
                 d = s.extract_descriptors()["hists"]
-                if path < 3:
+                if path != 3:
                     assert np.array_equal(d, base), path
                 else:
                     assert rel_l2(d, base).max() <= 1e-6
         finally:
             cu.s3d_set_option(eng, b"desc_path", 0)
+    # the same on anisotropic, non-dyadic units and on white noise (dense keypoints)
+    rng = np.random.default_rng(5)
+    for vol, units in ((blob_volume((48, 52, 60), seed=23), (1.0, 1.3, 0.8)),
+                       (rng.random((40, 44, 48), dtype=np.float32), (1.0, 1.0, 1.0))):
+        with capi.Sift3D(b200_lib) as s:
+            kp = s.detect_keypoints(vol, units=units)
+            if len(kp) == 0:
+                continue
+            eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+            base = s.extract_descriptors()["hists"].copy()
+            try:
+                assert cu.s3d_set_option(eng, b"desc_path", 4) == 0
+                assert np.array_equal(s.extract_descriptors()["hists"], base)
+            finally:
+                cu.s3d_set_option(eng, b"desc_path", 0)
