@@ -460,6 +460,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // orient_core for an integer centre with a weight table: same voxels, same order, same values.
+// BATCH = 4: four voxels fetched ahead; BATCH = 8: batches end on the 128-byte lines of the
+// gradient volume, so the loads of a batch are ONE L2 request however little of the line
+// survives in L1 between batches (1024 threads x their own lines thrash it).
+template <int BATCH>
 __device__ __forceinline__ bool orient_core_tab(const float *__restrict__ im, int nx, int ny,
                                                 int nz, float uxf, float uyf, float uzf, int cx,
                                                 int cy, int cz, double sigma,
@@ -503,19 +507,23 @@ __device__ __forceinline__ bool orient_core_tab(const float *__restrict__ im, in
             };
             if (gim) {
                 const float4 *grow = gim + roff;
-                for (int x = x0; x <= x1; x += 4) {
-                    float w[4];
-                    float4 g4[4];
+                for (int x = x0; x <= x1;) {
+                    // BATCH 8: up to the end of the current 128-byte line (8 float4)
+                    const int nb = BATCH == 8 ? min(8 - (int)((roff + (size_t)x) & 7), x1 - x + 1)
+                                              : min(4, x1 - x + 1);
+                    float w[BATCH];
+                    float4 g4[BATCH];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) w[k] = x + k <= x1 ? __ldg(trow + x + k) : -1.0f;
+                    for (int k = 0; k < BATCH; k++) w[k] = k < nb ? __ldg(trow + x + k) : -1.0f;
                     // gradients only inside the sphere (48 % of the box is outside): the window
                     // traffic, 16 B per visited voxel from L2, is what bounds this kernel
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
+                    for (int k = 0; k < BATCH; k++)
                         g4[k] = w[k] >= 0.0f ? __ldg(grow + x + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
+                    for (int k = 0; k < BATCH; k++)
                         if (w[k] >= 0.0f) acc(w[k], g4[k].x, g4[k].y, g4[k].z);
+                    x += nb;
                 }
             } else {
                 for (int x = x0; x <= x1; x++) {
@@ -536,8 +544,8 @@ __device__ __forceinline__ bool orient_core_tab(const float *__restrict__ im, in
 // TAB = true: detector candidates only (integer centres, sd == level scale, a table for every
 // keypoint level -- the launcher guarantees it); a separate instantiation so that the literal
 // path's f64 exp does not cost the fast one its occupancy.
-template <bool TAB>
-__global__ void __launch_bounds__(128, TAB ? 8 : 4)
+template <bool TAB, int BATCH = 4>
+__global__ void __launch_bounds__(128, TAB ? (BATCH == 8 ? 6 : 8) : 4)
     k_orient(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
              double corner_thresh, unsigned char *__restrict__ ok, double *__restrict__ conf_out,
              const OriTab *__restrict__ tabs, const float *__restrict__ pool)
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(128, TAB ? 8 : 4)
     const float zl = local_z(T, lv, c.z);
     bool accept;
     if (TAB)
-        accept = orient_core_tab(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
+        accept = orient_core_tab<BATCH>(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1], T.dims[3 * lv + 2],
                                  T.units[3 * lv], T.units[3 * lv + 1], T.units[3 * lv + 2],
                                  (int)c.x, (int)c.y, (int)zl, sig_fctr * c.sd, pool + tabs[lv].off,
                                  tabs[lv], T.gptrs ? T.gptrs[lv] : nullptr, corner_thresh, R, conf);
@@ -1775,13 +1783,19 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
         const PyrTable T = make_table(e);
         const int trc = build_orient_tables(e, T, 1.5);
         if (trc < 0) return -1;
-        if (trc == 0)  // every keypoint level has a table
-            k_orient<true><<<(n + 127) / 128, 128, 0, e->stream>>>(
-                e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
-                static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool);
-        else
+        if (trc == 0) {  // every keypoint level has a table
+            if (e->opt_orient_batch == 8)
+                k_orient<true, 8><<<(n + 127) / 128, 128, 0, e->stream>>>(
+                    e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
+                    static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool);
+            else
+                k_orient<true, 4><<<(n + 127) / 128, 128, 0, e->stream>>>(
+                    e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
+                    static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool);
+        } else {
             k_orient<false><<<(n + 127) / 128, 128, 0, e->stream>>>(
                 e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr, nullptr, nullptr);
+        }
         S3D_LAUNCH_CHECK(e);
     }
     k_flag_scan<<<1, 1024, 0, e->stream>>>(e->d_ok, n, e->d_pos, e->d_counter);
