@@ -75,6 +75,7 @@ struct s3d_engine {
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
     int opt_orient_batch = 4;  // voxels k_orient fetches ahead (4, or 8 = line-aligned batches)
+    int opt_desc_norot = 0;  // 1: no lane-dependent vertex order in k_descriptor2 (A/B only)
     int opt_desc_occ = 4;   // CTAs per SM k_descriptor2 is compiled for (3 or 4)
     int opt_desc_path = 0;  // test hook: force a fixed-point path of k_descriptor2 (0 = automatic)
     double blur_w[4] = {1.05, 1.10, 1.05, 1.10};  // per-plane cost of edge columns (left,right,top,bottom)

@@ -167,6 +167,7 @@ int s3d_engine_create(s3d_engine **out, int device)
     if (const char *v = getenv("S3D_BLUR_MODE")) e->blur_mode = atoi(v);
     if (const char *v = getenv("S3D_DENSE_COPY")) e->opt_dense_copy = atoi(v);
     if (const char *v = getenv("S3D_DESC_OCC")) e->opt_desc_occ = atoi(v);
+    if (const char *v = getenv("S3D_DESC_NOROT")) e->opt_desc_norot = atoi(v);
     if (const char *v = getenv("S3D_ORIENT_BATCH")) e->opt_orient_batch = atoi(v);
     if ((ce = cudaMalloc(&e->d_counter, 4 * sizeof(int))) != cudaSuccess) {
         s3d_fail(nullptr, "cudaMalloc", ce, __FILE__, __LINE__);
@@ -235,6 +236,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
     else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
+    else if (!strcmp(name, "desc_norot")) e->opt_desc_norot = value;
     else if (!strcmp(name, "orient_batch")) e->opt_orient_batch = value;
     else if (!strcmp(name, "blur_dbg")) {
         DeviceGuard guard(e->device);

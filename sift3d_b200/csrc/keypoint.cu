@@ -75,6 +75,13 @@ struct FaceSh {
         asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(la + 4u * (unsigned)i));
         return v;
     }
+    // word at a run-time byte offset of a FaceConst (vertex indices in a rotated order)
+    __device__ __forceinline__ int word(int face, unsigned byte_off) const
+    {
+        int v;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(fa + (unsigned)face * (unsigned)sizeof(FaceConst) + byte_off));
+        return v;
+    }
 };
 
 // cart2bary (sift.c:335-394) with the per-face constants hoisted.
@@ -971,6 +978,13 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
     // path, 3 = legacy 2^-32 / 64-bit carry path -- all must agree with the default
     const int force_path = HOOK ? (icos_fast >> 1) & 3 : 0;
     const bool trim = !(HOOK && (icos_fast & 8));  // test hook: leave the row intervals untrimmed
+    // Lane-dependent order of the three vertex updates of a corner: lanes whose voxels fall into
+    // the same cell and face (neighbouring rows of a smooth volume) would otherwise hit the SAME
+    // address in every one of the 24 ATOMS and serialise; rotated, they hit three different bins.
+    // (bit 4 of the flags switches the rotation off: A/B measurements.)
+    const int rot = (icos_fast & 16) ? 0 : lane % 3;
+    const unsigned rk0 = 4u * (unsigned)(13 + rot), rk1 = 4u * (unsigned)(13 + (rot + 1) % 3),
+                   rk2 = 4u * (unsigned)(13 + (rot + 2) % 3);
     icos_fast &= 1;
     if (force_path == 3) split = false;
     if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
@@ -1181,7 +1195,13 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
                 dv[a] = fs(vb[a], floorf(vb[a]));
                 ib[a] = (int)vb[a];
             }
-            const int i0 = faces.idx<0>(bin), i1 = faces.idx<1>(bin), i2 = faces.idx<2>(bin);
+            const int i0 = faces.word(bin, rk0), i1 = faces.word(bin, rk1), i2 = faces.word(bin, rk2);
+            {  // the barycentric weights in the same rotated order
+                const float t0 = bary[0], t1 = bary[1], t2 = bary[2];
+                bary[0] = rot == 0 ? t0 : (rot == 1 ? t1 : t2);
+                bary[1] = rot == 0 ? t1 : (rot == 1 ? t2 : t0);
+                bary[2] = rot == 0 ? t2 : (rot == 1 ? t0 : t1);
+            }
             // mag * 2^S: scaling by a power of two commutes with every rounding below, so
             // fm(fm(mag_s, wgt), bary) == fm(fm(mag, wgt), bary) * 2^S (sift.c:1763-1765)
             const float mag_s = fm(mag, split ? fx_scale : 4294967296.0f);
@@ -1824,8 +1844,8 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
         k_descriptor2<3, false><<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
                                                                    e->opt_icos_fast & 1);
     else
-        k_descriptor2<4, false><<<n, DESC2_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out,
-                                                                   e->opt_icos_fast & 1);
+        k_descriptor2<4, false><<<n, DESC2_THREADS, 0, e->stream>>>(
+            d_kp, n, T, e->d_mesh, d_out, (e->opt_icos_fast & 1) | (e->opt_desc_norot ? 16 : 0));
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
