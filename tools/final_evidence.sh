@@ -14,8 +14,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1700 --csv --log-fi
     python bench.py --steps 1 --warmup 2 --no-cpu-baseline --blur-reps 1 > $out/bench_under_ncu.log 2>&1
 S3D_TRACE=1 timeout 300 python tools/dense_time.py 256 > $out/dense_256.txt 2>&1
 timeout 300 python tools/e2e_breakdown.py 512 > $out/e2e_breakdown.txt 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"k_conv_dyadic|k_extrema_mark|k_extrema_emit" -c 14 --csv --page raw \
-    --log-file $out/ncu_dyadic_extrema.csv python tools/run_desc.py 256 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"k_conv_dyadic|k_extrema_mark" -c 37 --csv --page raw \
+    --log-file $out/ncu_dyadic_extrema.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --blur-reps 1 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_descriptor2 -s 1 -c 1 -o $out/desc \
+    python tools/run_desc.py 192 > $out/ncu_desc.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_run.py > $out/sanitizer_memcheck.txt 2>&1
 echo "memcheck rc=$?" >> $out/sanitizer_memcheck.txt
 ls -la $out
