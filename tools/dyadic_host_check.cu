@@ -105,9 +105,38 @@ static int check(int nx, int ny, int nz, unsigned seed)
     return bad != 0;
 }
 
+// interleaved channels: the x pass is a "y" pass over lines of stride nc, y / z see rows of nx*nc
+template <int HW>
+static int check_nc(int nx, int ny, int nz, int nc, unsigned seed)
+{
+    const size_t n = (size_t)nx * ny * nz * nc;
+    std::vector<float> src(n), a(n), b(n), c(n), ref(n);
+    srand(seed);
+    for (size_t i = 0; i < n; i++) src[i] = (float)rand() / (float)RAND_MAX - 0.3f;
+    TapSet taps;
+    memset(&taps, 0, sizeof(taps));
+    taps.width = orc_gauss_taps(HW / 3.0 - 1e-3, taps.t, S3D_MAX_TAPS);
+    if (taps.width != 2 * HW + 1) { printf("width %d != %d\n", taps.width, 2 * HW + 1); return 1; }
+    const double units[3] = {1.0, 1.0, 1.0};
+    orc_blur(src.data(), ref.data(), nx, ny, nz, nc, units, taps.t, taps.width, 1.0);
+    host_axis<1, 0, HW, 16>(src.data(), a.data(), nc, nx, ny * nz, taps);
+    host_axis<1, 0, HW, 16>(a.data(), b.data(), nx * nc, ny, nz, taps);
+    host_axis<2, 0, HW, 16>(b.data(), c.data(), nx * nc, ny, nz, taps);
+    size_t bad = 0;
+    for (size_t i = 0; i < n; i++) bad += memcmp(&c[i], &ref[i], 4) != 0;
+    printf("nc=%d HW=%d %dx%dx%d: %zu / %zu differ\n", nc, HW, nx, ny, nz, bad, n);
+    return bad != 0;
+}
+
 int main()
 {
     int rc = 0;
+    rc |= check_nc<9>(22, 20, 18, 12, 41);
+    rc |= check_nc<7>(9, 21, 19, 12, 42);
+    rc |= check_nc<10>(25, 12, 23, 3, 43);
+    rc |= check<0, 9>(41, 22, 20, 44);
+    rc |= check<0, 7>(300, 9, 17, 45);
+    rc |= check<0, 10>(23, 24, 25, 46);
     rc |= check<0, 2>(37, 21, 19, 21);
     rc |= check<0, 3>(13, 21, 19, 22);
     rc |= check<0, 8>(37, 18, 41, 23);
