@@ -357,6 +357,113 @@ __global__ void __launch_bounds__(EXT_BLOCK, KT > 0 ? 3 : 1)
     if (threadIdx.x < K) blockcnt[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
+// Pass A for row lengths that are a multiple of 4 (K == 3): a thread owns FOUR consecutive
+// voxels of one row -- one aligned 16-byte load per level and neighbour direction instead of
+// four 4-byte ones, the x neighbours come out of the same registers -- and the strict
+// 8-neighbour tests are one max and one min over the neighbours (FMNMX3) and two compares.
+// Eight lanes assemble a 32-voxel mask word with three shuffles.  Same masks, same counts.
+__global__ void __launch_bounds__(EXT_BLOCK, 3)
+    k_extrema_mark4(const ExtLevels L, int nx, int ny, int nz, double peak_thresh,
+                    unsigned *__restrict__ mask, int *__restrict__ blockcnt, int nblocks,
+                    size_t words_per_level)
+{
+    constexpr int K = 3;
+    const size_t total = (size_t)nx * ny * nz;
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    const size_t base = (size_t)blockIdx.x * EXT_CHUNK;
+    __shared__ int s_cnt[EXT_MAX_LEVELS];
+    if (threadIdx.x < EXT_MAX_LEVELS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    float thr[K];
+#pragma unroll
+    for (int s = 0; s < K; s++)  // thr = (float)(peak_thresh * dogmax), sift.c:1169
+        thr[s] = (float)(peak_thresh * (double)__uint_as_float(L.maxbits[s + 1]));
+    int cnt[K] = {0, 0, 0};
+    const int lane = threadIdx.x & 31;
+    for (int it = 0; it < EXT_CHUNK / (4 * EXT_BLOCK); it++) {
+        const size_t idx = base + 4 * ((size_t)it * EXT_BLOCK + threadIdx.x);  // first of 4 voxels
+        if (base + 4 * (size_t)it * EXT_BLOCK >= total) break;                // block-uniform
+        bool row_in = false;
+        int x = 0;
+        if (idx < total) {
+            int y, z;
+            if (total < 0xffffffffull) {  // 32-bit divisions
+                const unsigned i32 = (unsigned)idx;
+                const unsigned r = i32 / (unsigned)nx;
+                x = (int)(i32 - r * (unsigned)nx);
+                z = (int)(r / (unsigned)ny);
+                y = (int)(r - (unsigned)z * (unsigned)ny);
+            } else {
+                x = (int)(idx % nx);
+                const size_t r = idx / nx;
+                y = (int)(r % ny);
+                z = (int)(r / ny);
+            }
+            row_in = y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2;
+        }
+        float4 v[K];
+#pragma unroll
+        for (int s = 0; s < K; s++)
+            v[s] = row_in ? __ldg(reinterpret_cast<const float4 *>(L.dog[s + 1] + idx))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < K; s++) {
+            const float c[4] = {v[s].x, v[s].y, v[s].z, v[s].w};
+            bool pass[4];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                pass[k] = row_in && x + k >= 1 && x + k <= nx - 2 && (c[k] > thr[s] || c[k] < -thr[s]);
+                any = any || pass[k];
+            }
+            unsigned nib = 0;
+            if (any) {
+                const float *cur = L.dog[s + 1] + idx;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 p = __ldg(reinterpret_cast<const float4 *>(L.dog[s] + idx));
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(L.dog[s + 2] + idx));
+                const float4 yp = __ldg(reinterpret_cast<const float4 *>(cur + ys));
+                const float4 ym = __ldg(reinterpret_cast<const float4 *>(cur - ys));
+                const float4 zp = __ldg(reinterpret_cast<const float4 *>(cur + zs));
+                const float4 zm = __ldg(reinterpret_cast<const float4 *>(cur - zs));
+                const float xl = x > 0 ? __ldg(cur - 1) : 0.0f;          // only used by voxel 0
+                const float xr = x + 4 < nx ? __ldg(cur + 4) : 0.0f;     // only used by voxel 3
+                (void)z4;
+                const float P[4] = {p.x, p.y, p.z, p.w}, Q[4] = {q.x, q.y, q.z, q.w};
+                const float YP[4] = {yp.x, yp.y, yp.z, yp.w}, YM[4] = {ym.x, ym.y, ym.z, ym.w};
+                const float ZP[4] = {zp.x, zp.y, zp.z, zp.w}, ZM[4] = {zm.x, zm.y, zm.z, zm.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float l = k == 0 ? xl : c[k - 1], r = k == 3 ? xr : c[k + 1];
+                    // strict extremum over the 6 + 1 + 1 neighbours (sift.c:1184-1190): c > all
+                    // <=> c > max, c < all <=> c < min (no NaNs in a DoG of finite data)
+                    const float mx = fmaxf(fmaxf(fmaxf(P[k], Q[k]), fmaxf(l, r)),
+                                           fmaxf(fmaxf(YP[k], YM[k]), fmaxf(ZP[k], ZM[k])));
+                    const float mn = fminf(fminf(fminf(P[k], Q[k]), fminf(l, r)),
+                                           fminf(fminf(YP[k], YM[k]), fminf(ZP[k], ZM[k])));
+                    if (pass[k] && (c[k] > mx || c[k] < mn)) nib |= 1u << k;
+                }
+            }
+            // eight lanes (32 voxels) -> one mask word
+            unsigned w = nib << (4 * (lane & 7));
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+            if ((lane & 7) == 0) {
+                mask[(size_t)s * words_per_level + (idx >> 5)] = w;
+                cnt[s] += __popc(w);
+            }
+        }
+    }
+    if ((lane & 7) == 0) {
+#pragma unroll
+        for (int s = 0; s < K; s++)
+            if (cnt[s]) atomicAdd(&s_cnt[s], cnt[s]);
+    }
+    __syncthreads();
+    if (threadIdx.x < K) blockcnt[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
 // Pass B: exclusive scan of the per-block counts, level after level, continuing
 // the running candidate total kept in counter[0].  One block.
 __global__ void __launch_bounds__(1024) k_extrema_scan(int *__restrict__ blockcnt, int nblocks,
@@ -641,7 +748,12 @@ int s3d_k_extrema_range(s3d_engine *e, int o, double peak_thresh, int zl0, int n
     for (int s = -1; s <= K; s++) L.dog[s + 1] = e->dog[(size_t)o * e->nlev_d + (s + 1)].d + zskip;
     L.maxbits = e->d_scalars + 1 + (size_t)o * e->nlev_d;
     L.K = K;
-    if (K == 3)
+    bool vec4 = K == 3 && (nx & 3) == 0 && e->blur_mode == 0;
+    for (int s = 0; s <= K + 1 && vec4; s++) vec4 = ((uintptr_t)L.dog[s] & 15) == 0;
+    if (vec4)
+        k_extrema_mark4<<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
+                                                             e->d_blockcnt, nblocks, words);
+    else if (K == 3)
         k_extrema_mark<3><<<nblocks, EXT_BLOCK, 0, e->stream>>>(L, nx, ny, nz, peak_thresh, e->d_mask,
                                                                e->d_blockcnt, nblocks, words);
     else
