@@ -193,6 +193,7 @@ int s3d_k_decimate(s3d_engine *e, const float *src, int sx, int sy, int sz, floa
                    int dy, int dz);
 int s3d_k_dog(s3d_engine *e, const float *a, const float *b, float *d, size_t n,
               unsigned *d_maxbits);
+int s3d_k_dog_octave(s3d_engine *e, int o);  // all DoG levels of an octave at once; 1 = not applicable
 int s3d_k_extrema_octave(s3d_engine *e, int o, float peak_thresh_dummy, double peak_thresh);
 // scan only local planes [zl0, zl0 + nzs) of the octave's DoG buffers as if they were a whole
 // volume (its first and last plane are neighbours only); emitted z = local-sub z + zbase

@@ -441,7 +441,10 @@ int s3d_build_pyramid(s3d_engine *e)
         }
     }
     // build_dog (sift.c:1052-1071) fused with the per-level max|DoG| (sift.c:1161-1166)
-    for (int o = 0; o < e->noct; o++)
+    for (int o = 0; o < e->noct; o++) {
+        const int drc = e->blur_mode == 0 ? s3d_k_dog_octave(e, o) : 1;
+        if (drc < 0) return -1;
+        if (drc == 0) continue;
         for (int s = -1; s <= e->nlev_d - 2; s++) {
             const LevelDev &a = e->g[(size_t)o * e->nlev_g + s + 1];
             const LevelDev &b = e->g[(size_t)o * e->nlev_g + s + 2];
@@ -449,6 +452,7 @@ int s3d_build_pyramid(s3d_engine *e)
             if (s3d_k_dog(e, a.d, b.d, d.d, a.n(), e->d_scalars + 1 + (size_t)o * e->nlev_d + s + 1))
                 return -1;
         }
+    }
     return 0;
 }
 

@@ -243,6 +243,58 @@ __global__ void __launch_bounds__(256) k_dog(const float *__restrict__ a,
     }
 }
 
+// All DoG levels of one octave in one pass: every Gaussian level is read ONCE (the per-level
+// kernel reads each inner level twice): (NL + NL-1) x 4 B/voxel instead of (NL-1) x 12.
+#define DOG_MAX_LEVELS 18
+struct DogLevels {
+    const float *g[DOG_MAX_LEVELS];
+    float *d[DOG_MAX_LEVELS - 1];
+    unsigned *maxbits;  // [NL-1] consecutive slots
+    int nl;
+};
+
+template <int NLT>  // NLT > 0: number of Gaussian levels known at compile time
+__global__ void __launch_bounds__(256) k_dog_octave(const DogLevels L, size_t n4)
+{   // n4 float4 groups (n % 4 == 0, 16-byte aligned levels: the launcher checks)
+    const int nl = NLT > 0 ? NLT : L.nl;
+    constexpr int NA = NLT > 0 ? NLT : DOG_MAX_LEVELS;
+    float m[NA - 1];
+#pragma unroll
+    for (int s = 0; s < NA - 1; s++) m[s] = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float4 v[NA];
+#pragma unroll
+        for (int s = 0; s < NA; s++)
+            if (s < nl) v[s] = __ldg(reinterpret_cast<const float4 *>(L.g[s]) + i);
+#pragma unroll
+        for (int s = 0; s < NA - 1; s++) {
+            if (s >= nl - 1) break;
+            float4 d;
+            d.x = __fsub_rn(v[s].x, v[s + 1].x);
+            d.y = __fsub_rn(v[s].y, v[s + 1].y);
+            d.z = __fsub_rn(v[s].z, v[s + 1].z);
+            d.w = __fsub_rn(v[s].w, v[s + 1].w);
+            reinterpret_cast<float4 *>(L.d[s])[i] = d;
+            m[s] = fmaxf(m[s], fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+        }
+    }
+    __shared__ float sm[8];
+#pragma unroll
+    for (int s = 0; s < NA - 1; s++) {
+        if (s >= nl - 1) break;
+        const float w = warp_max(m[s]);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = w;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float t = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0f;
+            t = warp_max(t);
+            if (threadIdx.x == 0) atomicMax(L.maxbits + s, __float_as_uint(t));
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- extrema
 // Pass A: every block scans EXT_CHUNK consecutive voxels of the octave (linear index = scan
 // order), all K keypoint levels; a warp handles 32 consecutive voxels per step and lane 0 writes
@@ -711,6 +763,34 @@ int s3d_k_dog(s3d_engine *e, const float *a, const float *b, float *d, size_t n,
 {
     k_dog<<<grid_for(e, n / 4 + 1, 256, 8), 256, 0, e->stream>>>(a, b, d, n, head_of(n, a, b, d),
                                                                  d_maxbits);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+// build_dog for one octave (levels consecutive in e->g / e->dog); returns 1 if the fused kernel
+// does not apply (the caller then runs s3d_k_dog per level)
+int s3d_k_dog_octave(s3d_engine *e, int o)
+{
+    const int nl = e->nlev_g;
+    if (nl < 2 || nl > DOG_MAX_LEVELS || e->nlev_d != nl - 1) return 1;
+    const size_t n = e->g[(size_t)o * nl].n();
+    if (n == 0 || (n & 3)) return 1;
+    DogLevels L;
+    L.nl = nl;
+    for (int s = 0; s < nl; s++) {
+        L.g[s] = e->g[(size_t)o * nl + s].d;
+        if (((uintptr_t)L.g[s] & 15) || e->g[(size_t)o * nl + s].n() != n) return 1;
+    }
+    for (int s = 0; s < nl - 1; s++) {
+        L.d[s] = e->dog[(size_t)o * e->nlev_d + s].d;
+        if (((uintptr_t)L.d[s] & 15) || e->dog[(size_t)o * e->nlev_d + s].n() != n) return 1;
+    }
+    L.maxbits = e->d_scalars + 1 + (size_t)o * e->nlev_d;
+    const int grid = grid_for(e, n / 4, 256, 8);
+    if (nl == 6)
+        k_dog_octave<6><<<grid, 256, 0, e->stream>>>(L, n / 4);
+    else
+        k_dog_octave<0><<<grid, 256, 0, e->stream>>>(L, n / 4);
     S3D_LAUNCH_CHECK(e);
     return 0;
 }
