@@ -293,6 +293,115 @@ __global__ void __launch_bounds__(256) k_conv_dyadic(const float *__restrict__ s
     }
 }
 
+// ---- z axis over a plane range of a Z-slab buffer ----------------------------------------------
+// The buffer holds planes [gbase, gbase + nbuf) of a line of nglob planes; outputs are the buffer
+// planes [zb, ze).  Sample coordinates, the interior range and the mirror are those of the GLOBAL
+// line (the f32 roundings of the mirror depend on the magnitude of the index, and a slab must
+// reproduce the whole-volume result bit for bit); only the addressing is shifted and clamped to
+// the buffer (an interior output never reaches outside it: the caller provides the halo).
+__host__ __device__ __forceinline__ float lit_samp_g(float acc, float tap, float c, const float *line,
+                                                     size_t st, int dim_end, int gbase, int nbuf)
+{
+    int lo = F2I_RZ(c);
+    const float frac = RSUB(c, (float)lo);
+    int hi = lo + 1;
+    lo = s3d_clampi(s3d_clampi(lo, dim_end) - gbase, nbuf - 1);
+    hi = s3d_clampi(s3d_clampi(hi, dim_end) - gbase, nbuf - 1);
+    const float v = RADD(RMUL(RSUB(1.0f, frac), LDG(line + (size_t)lo * st)),
+                         RMUL(frac, LDG(line + (size_t)hi * st)));
+    return RADD(acc, RMUL(tap, v));
+}
+
+__host__ __device__ __noinline__ float boundary_point_g(const float *line, size_t st, int nglob, int i,
+                                                        const TapSet &taps, float uf, int gbase,
+                                                        int nbuf)
+{
+    const int hw = taps.width / 2;
+    const int dim_end = nglob - 1;
+    float acc = 0.0f;
+    for (int d = -hw; d <= hw; d++) {
+        const float step = RMUL((float)d, uf);
+        float c = RSUB((float)i, step);
+        if (F2I_RZ(c) < 0)
+            c = -c;
+        else if (F2I_RZ(c) >= dim_end)
+            c = RSUB(RSUB(RMUL(2.0f, (float)dim_end), c), 0.1f);
+        acc = lit_samp_g(acc, taps.t[d + hw], c, line, st, dim_end, gbase, nbuf);
+    }
+    return acc;
+}
+
+// one thread's RUN outputs starting at buffer plane b0 of the line at `line` (buffer plane 0)
+template <int O, int HW, int RUN>
+__host__ __device__ __forceinline__ void zrange_run(const float *line, float *out, size_t plane,
+                                                    int nbuf, int b0, int ze, int gbase, int nglob,
+                                                    const TapSet &taps)
+{
+    constexpr int P = 1 << O;
+    constexpr int UHW = (HW + P - 1) >> O;
+    float acc[RUN];
+    conv_run_ld<O, HW, RUN>(
+        [&](int jj) { return LDG(line + (size_t)s3d_clampi(b0 + jj, nbuf - 1) * plane); }, taps, acc);
+    const int i0 = gbase + b0;  // global index of the first output
+    const int start = UHW, end = nglob - 1 - (UHW + 1);
+    if (i0 < start || i0 + RUN - 1 > end) {
+#pragma unroll
+        for (int k = 0; k < RUN; k++) {
+            const int i = i0 + k;
+            if (b0 + k < ze && (i < start || i > end))
+                acc[k] = boundary_point_g(line, plane, nglob, i, taps, 1.0f / (float)P, gbase, nbuf);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RUN; k++)
+        if (b0 + k < ze) out[(size_t)(b0 + k) * plane] = acc[k];
+}
+
+template <int O, int HW, int RUN>
+__global__ void __launch_bounds__(256) k_conv_dyadic_zr(const float *__restrict__ src,
+                                                        float *__restrict__ dst, int nx, int ny,
+                                                        int nbuf, int zb, int ze, int gbase, int nglob,
+                                                        const __grid_constant__ TapSet taps)
+{
+    const size_t plane = (size_t)nx * ny;
+    const size_t nruns = (size_t)(ze - zb + RUN - 1) / RUN;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < plane * nruns;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const size_t line_off = t % plane;
+        const int b0 = zb + (int)(t / plane) * RUN;
+        zrange_run<O, HW, RUN>(src + line_off, dst + line_off, plane, nbuf, b0, ze, gbase, nglob, taps);
+    }
+}
+
+template <int O, int HW>
+int launch_zr(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nbuf, int zb, int ze,
+              int gbase, int nglob, const TapSet &taps)
+{
+    constexpr int RUN = 16;
+    const size_t nthreads = (size_t)nx * ny * ((size_t)(ze - zb + RUN - 1) / RUN);
+    const size_t want = (nthreads + 255) / 256;
+    const size_t cap = (size_t)e->num_sms * 64;
+    const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+    k_conv_dyadic_zr<O, HW, RUN><<<grid, 256, 0, e->stream>>>(src, dst, nx, ny, nbuf, zb, ze, gbase,
+                                                             nglob, taps);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
+template <int O>
+int launch_zr_hw(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nbuf, int zb, int ze,
+                 int gbase, int nglob, const TapSet &taps)
+{
+    switch (taps.width / 2) {
+    case 3: return launch_zr<O, 3>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
+    case 4: return launch_zr<O, 4>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
+    case 5: return launch_zr<O, 5>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
+    case 6: return launch_zr<O, 6>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
+    case 8: return launch_zr<O, 8>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
+    default: return 1;
+    }
+}
+
 template <int AXIS, int O, int HW>
 int launch_one(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz,
                const TapSet &taps)
@@ -368,5 +477,15 @@ int s3d_conv_dyadic_axis(s3d_engine *e, int axis, int order, const float *src, f
     S3D_DY_ORDER(1)
     S3D_DY_ORDER(2)
 #undef S3D_DY_ORDER
+    return 1;
+}
+
+// z pass over the buffer planes [zb, ze) of a Z-slab buffer (see k_conv_dyadic_zr); order 1 or 2;
+// returns 1 if not instantiated, -1 on a launch error
+int s3d_conv_dyadic_zrange(s3d_engine *e, int order, const float *src, float *dst, int nx, int ny,
+                           int nbuf, int zb, int ze, int gbase, int nglob, const TapSet &taps)
+{
+    if (order == 1) return launch_zr_hw<1>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
+    if (order == 2) return launch_zr_hw<2>(e, src, dst, nx, ny, nbuf, zb, ze, gbase, nglob, taps);
     return 1;
 }

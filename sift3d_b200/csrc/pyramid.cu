@@ -663,6 +663,8 @@ bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps,
 int s3d_conv_dyadic_order(const TapSet &taps, float uf, int n);  // blur_dyadic.cu
 int s3d_conv_dyadic_axis(s3d_engine *e, int axis, int order, const float *src, float *dst, int nx,
                          int ny, int nz, const TapSet &taps);
+int s3d_conv_dyadic_zrange(s3d_engine *e, int order, const float *src, float *dst, int nx, int ny,
+                           int nbuf, int zb, int ze, int gbase, int nglob, const TapSet &taps);
 
 int s3d_k_blur(s3d_engine *e, const float *src, float *dst, int nx, int ny, int nz, int nc,
                const TapSet &taps, const float uf[3])
@@ -735,16 +737,43 @@ int s3d_k_blur_zrange(s3d_engine *e, const float *src, float *dst, int nx, int n
     const size_t sub = plane * (size_t)(p1 - p0);
     if (s3d_ensure_scratch(e, sub)) return -1;
     const int grid = grid_for(e, sub, 256, 16);
-    k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src + plane * p0, e->scratch[0], nx, ny, p1 - p0, 1,
-                                               taps, uf[0], 0, 0, 0, 0, is_dyadic(uf[0], nx));
-    S3D_LAUNCH_CHECK(e);
-    k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, p1 - p0, 1,
-                                               taps, uf[1], 0, 0, 0, 0, is_dyadic(uf[1], ny));
-    S3D_LAUNCH_CHECK(e);
-    k_conv_axis<2><<<grid_for(e, plane * (size_t)(ze - zb), 256, 16), 256, 0, e->stream>>>(
-        e->scratch[1], dst + plane * zb, nx, ny, ze - zb, 1, taps, uf[2], zb - p0, p1 - p0,
-        gz0 + p0, nz_glob, is_dyadic(uf[2], nz_glob));
-    S3D_LAUNCH_CHECK(e);
+    // octaves 1 and 2 of a dyadic pyramid: the register-blocked kernels (blur_dyadic.cu); x and y
+    // are plain passes over the planes [p0, p1), z takes the plane-range variant
+    int ord[3] = {-1, -1, -1};
+    if (e->blur_mode == 0) {
+        ord[0] = s3d_conv_dyadic_order(taps, uf[0], nx);
+        ord[1] = s3d_conv_dyadic_order(taps, uf[1], ny);
+        ord[2] = s3d_conv_dyadic_order(taps, uf[2], nz_glob);
+    }
+    int rc = 1;
+    if (ord[0] >= 1)
+        rc = s3d_conv_dyadic_axis(e, 0, ord[0], src + plane * p0, e->scratch[0], nx, ny, p1 - p0, taps);
+    if (rc < 0) return -1;
+    if (rc) {
+        k_conv_axis<0><<<grid, 256, 0, e->stream>>>(src + plane * p0, e->scratch[0], nx, ny, p1 - p0,
+                                                   1, taps, uf[0], 0, 0, 0, 0, is_dyadic(uf[0], nx));
+        S3D_LAUNCH_CHECK(e);
+    }
+    rc = 1;
+    if (ord[1] >= 1)
+        rc = s3d_conv_dyadic_axis(e, 1, ord[1], e->scratch[0], e->scratch[1], nx, ny, p1 - p0, taps);
+    if (rc < 0) return -1;
+    if (rc) {
+        k_conv_axis<1><<<grid, 256, 0, e->stream>>>(e->scratch[0], e->scratch[1], nx, ny, p1 - p0, 1,
+                                                   taps, uf[1], 0, 0, 0, 0, is_dyadic(uf[1], ny));
+        S3D_LAUNCH_CHECK(e);
+    }
+    rc = 1;
+    if (ord[2] >= 1)  // scratch[1] holds planes [p0, p1) = global [gz0 + p0, gz0 + p1)
+        rc = s3d_conv_dyadic_zrange(e, ord[2], e->scratch[1], dst + plane * p0, nx, ny, p1 - p0,
+                                    zb - p0, ze - p0, gz0 + p0, nz_glob, taps);
+    if (rc < 0) return -1;
+    if (rc) {
+        k_conv_axis<2><<<grid_for(e, plane * (size_t)(ze - zb), 256, 16), 256, 0, e->stream>>>(
+            e->scratch[1], dst + plane * zb, nx, ny, ze - zb, 1, taps, uf[2], zb - p0, p1 - p0,
+            gz0 + p0, nz_glob, is_dyadic(uf[2], nz_glob));
+        S3D_LAUNCH_CHECK(e);
+    }
     return 0;
 }
 

@@ -105,6 +105,38 @@ static int check(int nx, int ny, int nz, unsigned seed)
     return bad != 0;
 }
 
+// z pass over a plane range of a slab buffer vs the same planes of the whole-volume z pass
+template <int O, int HW>
+static int check_zr(int nx, int ny, int nz, unsigned seed)
+{
+    constexpr int P = 1 << O, H = ((HW + P - 1) >> O) + 1;
+    const size_t plane = (size_t)nx * ny, n = plane * nz;
+    std::vector<float> src(n), whole(n);
+    srand(seed);
+    for (size_t i = 0; i < n; i++) src[i] = (float)rand() / (float)RAND_MAX - 0.3f;
+    TapSet taps;
+    memset(&taps, 0, sizeof(taps));
+    taps.width = orc_gauss_taps(HW / 3.0 - 1e-3, taps.t, S3D_MAX_TAPS);
+    host_axis<2, O, HW, 16>(src.data(), whole.data(), nx, ny, nz, taps);
+    size_t bad = 0, cnt = 0;
+    const int ranges[4][2] = {{0, nz / 3}, {nz / 3, 2 * nz / 3 + 1}, {2 * nz / 3 + 1, nz}, {0, nz}};
+    for (auto &rg : ranges) {
+        const int o0 = rg[0], o1 = rg[1];                       // global output planes
+        const int g0 = o0 - H < 0 ? 0 : o0 - H, g1 = o1 + H > nz ? nz : o1 + H;  // buffer = outputs + halo
+        const int nbuf = g1 - g0, zb = o0 - g0, ze = o1 - g0;
+        std::vector<float> buf(src.begin() + plane * g0, src.begin() + plane * g1), out(plane * nbuf, -555.0f);
+        const size_t nruns = (size_t)(ze - zb + 15) / 16;
+        for (size_t t = 0; t < plane * nruns; t++)
+            zrange_run<O, HW, 16>(buf.data() + t % plane, out.data() + t % plane, plane, nbuf,
+                                  zb + (int)(t / plane) * 16, ze, g0, nz, taps);
+        for (int z = o0; z < o1; z++)
+            for (size_t i = 0; i < plane; i++, cnt++)
+                bad += memcmp(&out[(size_t)(z - g0) * plane + i], &whole[(size_t)z * plane + i], 4) != 0;
+    }
+    printf("zrange O=%d HW=%d %dx%dx%d: %zu / %zu differ\n", O, HW, nx, ny, nz, bad, cnt);
+    return bad != 0;
+}
+
 // interleaved channels: the x pass is a "y" pass over lines of stride nc, y / z see rows of nx*nc
 template <int HW>
 static int check_nc(int nx, int ny, int nz, int nc, unsigned seed)
@@ -131,6 +163,11 @@ static int check_nc(int nx, int ny, int nz, int nc, unsigned seed)
 int main()
 {
     int rc = 0;
+    rc |= check_zr<1, 8>(9, 7, 41, 51);
+    rc |= check_zr<1, 3>(5, 6, 37, 52);
+    rc |= check_zr<2, 8>(6, 5, 40, 53);
+    rc |= check_zr<2, 5>(4, 9, 23, 54);
+    rc |= check_zr<1, 6>(7, 3, 12, 55);
     rc |= check_nc<9>(22, 20, 18, 12, 41);
     rc |= check_nc<7>(9, 21, 19, 12, 42);
     rc |= check_nc<10>(25, 12, 23, 3, 43);
