@@ -994,42 +994,21 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
 
     const int bx = max(x1 - x0 + 1, 0), by = max(y1 - y0 + 1, 0), bz = max(z1 - z0 + 1, 0);
     const int nrows = by * bz;
-    const int rows_per_batch = 0;
-    const int bx_safe = max(bx, 1);
     const size_t ys = nx, zs = (size_t)nx * ny;
-
-    // spatial-bin coordinates of a voxel; false if outside the sphere or the descriptor cube
-    auto geom = [&](int x, int y, int z, float &sq, float vb[3]) -> bool {
-        const float vx = fm(fs((float)x, kp.x), uxf);
-        const float vy = fm(fs((float)y, kp.y), uyf);
-        const float vz = fm(fs((float)z, kp.z), uzf);
-        sq = fa(fa(fm(vx, vx), fm(vy, vy)), fm(vz, vz));
-        if (sq > r2) return false;
-        bool inside = true;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const float vk = dot3(Rt[3 * a], vx, Rt[3 * a + 1], vy, Rt[3 * a + 2], vz);
-            vb[a] = fm(fa(vk, half), bin_fctr);
-            inside = inside && !(vb[a] < 0.0f || vb[a] >= 4.0f);
-        }
-        return inside;
-    };
 
     // Every warp works alone until the final reduction: it owns the rows w, w+8, w+16, ... of
     // the window box (interleaved for balance), 32 rows per chunk.
-    //   phase A (lane = row): the voxels of a row that can pass the reference's sphere and
-    //     descriptor-cube tests form ONE x interval -- the sphere chord intersected with the three
-    //     slabs 0 <= vb[a] < 4, each linear in x -- computed here in approximate arithmetic and
-    //     widened to whole voxels, so no per-voxel work is spent on selection;
+    //   phase A (lane = row): the voxels of a row that pass the reference's sphere and
+    //     descriptor-cube tests form ONE x interval -- a superset from the sphere chord
+    //     intersected with the three slabs 0 <= vb[a] < 4 (each linear in x) in approximate
+    //     arithmetic, trimmed to the exact interval with the exact tests; the row's constants
+    //     are left in shared memory;
     //   phase B (lane = a contiguous share of the chunk's voxels, so that its consecutive voxels
-    //     are x neighbours while the 32 lanes sit in different rows): the full per-voxel work,
-    //     starting with the EXACT tests in the reference's f32 operation order, which reject the
-    //     few voxels the widening let through.
+    //     are x neighbours while the 32 lanes sit in different rows): the per-voxel work in the
+    //     reference's f32 operation order (the exact tests are kept as guards; nothing fails them).
     // Only __syncwarp between the phases; the static split makes the whole computation
     // deterministic (and the fixed-point histogram makes it order-independent anyway).
     constexpr int NWARP = DESC2_THREADS / 32;
-    (void)rows_per_batch;
-    (void)bx_safe;
     int4 *rows = s_rows[warp];
     const int my_rows = bx > 0 && nrows > warp ? (nrows - warp + NWARP - 1) / NWARP : 0;
     // slab a: vb = (sl[a] * dxv + off_row[a]) with dxv = x - kp.x in voxels
