@@ -861,26 +861,27 @@ struct D2Smem {
 
 // Descriptor, version 2 (the default).  One CTA (8 warps) per keypoint; every warp owns every
 // 8th row of the window's bounding box, 32 rows per chunk:
-//   phase A  (lane = row) the x interval of the row that can pass the reference's sphere /
-//            descriptor-cube tests -- sphere chord intersected with three slabs linear in x --
-//            in approximate arithmetic, widened to whole voxels; a warp scan of the interval
-//            lengths gives every voxel of the chunk an index;
+//   phase A  (lane = row) the x interval of the row that passes the reference's sphere /
+//            descriptor-cube tests: a superset (sphere chord intersected with three slabs linear
+//            in x, approximate arithmetic, widened) trimmed with the exact tests, which are weakly
+//            monotone in x under IEEE rounding; the row's constants go to shared memory; a warp
+//            scan of the interval lengths gives every voxel of the chunk an index;
 //   phase B  (lane = a contiguous share of those indices: its consecutive voxels are x
-//            neighbours, the 32 lanes sit in different rows) the full per-voxel work: the EXACT
-//            tests, gradient, glibc-exact window weight, rotation, icosahedron bin, 24 histogram
-//            updates.
+//            neighbours, the 32 lanes sit in different rows) the per-voxel work: gradient,
+//            glibc-exact window weight, rotation, icosahedron bin, 24 histogram updates.
 // The histogram is FIXED POINT: integer addition is associative, so the descriptor is
 // bit-reproducible from run to run (and between a tiled and a whole-volume run), and only
 // native 32-bit shared atomics are needed (f32 / 64-bit shared atomics are CAS loops in SASS).
 // A contribution c * 2^S (S chosen per keypoint so that |c * 2^S| < 2^31) is rounded to an
 // int32 q and added to a lo/hi word pair:
-//   FX_CARRY = 1: lo += q (mod 2^32) with ONE ATOMS whose returned old value gives the carry;
-//     hi += sign(q) + carry, which is almost always zero (no second atomic).  The three updates
-//     of a corner are issued together so their round trips overlap.
+//   FX_CARRY = 1: lo += q (mod 2^32) with ONE ATOMS whose returned old value gives the carry.
+//     Non-negative q (the common case): straight-line code over the 8 corners of a 5x5x5-padded
+//     cell grid (immediate address offsets), the 24 carry-outs collected in a mask and applied
+//     to the hi words after the voxel.  Signed q: hi += sign(q) + carry, a compact loop.
 //   FX_CARRY = 0: two fire-and-forget ATOMS, lo += q & 0xffff and hi += q >> 16 (arithmetic
 //     shift, so q == hi * 65536 + lo for negative q too); needs < 32768 contributions per bin,
 //     checked per keypoint from the size of a cell's support.  Fewer instructions but twice the
-//     shared-memory wavefronts, which is what bounds this kernel (ncu: LSU data pipe 83 %).
+//     shared-memory wavefronts, which is what bounds this kernel.
 // Windows too large for either take the 2^-32 / explicit 64-bit carry path.
 #define DESC2_THREADS 256
 #ifndef FX_CARRY
