@@ -74,6 +74,8 @@ struct s3d_engine {
     int blur_mode = 0;
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
+    int opt_orient_stage = 0;  // 1: k_orient_stage (experimental, unmeasured) instead of k_orient
+    int ori_max_twx = 0;       // widest weight-table row of the current orientation tables
     int opt_orient_batch = 4;  // voxels k_orient fetches ahead (4, or 8 = line-aligned batches)
     int opt_desc_norot = 0;  // 1: no lane-dependent vertex order in k_descriptor2 (A/B only)
     int opt_desc_occ = 4;   // CTAs per SM k_descriptor2 is compiled for (3 or 4)

@@ -169,6 +169,7 @@ int s3d_engine_create(s3d_engine **out, int device)
     if (const char *v = getenv("S3D_DESC_OCC")) e->opt_desc_occ = atoi(v);
     if (const char *v = getenv("S3D_DESC_NOROT")) e->opt_desc_norot = atoi(v);
     if (const char *v = getenv("S3D_ORIENT_BATCH")) e->opt_orient_batch = atoi(v);
+    if (const char *v = getenv("S3D_ORIENT_STAGE")) e->opt_orient_stage = atoi(v);
     if ((ce = cudaMalloc(&e->d_counter, 4 * sizeof(int))) != cudaSuccess) {
         s3d_fail(nullptr, "cudaMalloc", ce, __FILE__, __LINE__);
         cudaStreamDestroy(e->own_stream);
@@ -238,6 +239,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
     else if (!strcmp(name, "desc_norot")) e->opt_desc_norot = value;
     else if (!strcmp(name, "orient_batch")) e->opt_orient_batch = value;
+    else if (!strcmp(name, "orient_stage")) e->opt_orient_stage = value;
     else if (!strcmp(name, "blur_dbg")) {
         DeviceGuard guard(e->device);
         if (value && !e->d_blur_dbg) {

@@ -587,6 +587,124 @@ __global__ void __launch_bounds__(128, TAB ? (BATCH == 8 ? 6 : 8) : 4)
     if (conf_out) conf_out[i] = conf;
 }
 
+// EXPERIMENTAL (option "orient_stage", default off; written at the end of round 1 without GPU
+// time left to measure it).  Same per-candidate arithmetic in the same order as k_orient<true>,
+// but the 32 candidates of a warp walk their windows in LOCKSTEP over the offset (dz, dy):
+//   * the weight row of an offset is the same for all of them (same level, integer centres):
+//     ONE coalesced load, its sphere chord [jlo, jhi] by ballot, rows without a chord skipped;
+//   * the 32 gradient rows are fetched COOPERATIVELY, one candidate's row per step with lanes
+//     = consecutive voxels (one coalesced request of <= 27 x 16 B instead of 27 requests of 32
+//     scattered sectors each), into a per-warp shared tile of odd pitch (LDS.128 conflict-free);
+//   * each lane then consumes ITS row from shared memory in ascending x -- the f32 window
+//     gradient and the f64 tensor sums see exactly the reference's sequence.
+// A warp whose candidates do not share one level (the seams of the candidate list), or whose
+// level has no gradient volume, takes the per-thread path.
+#define ORI_STAGE_WARPS 2
+__global__ void __launch_bounds__(32 * ORI_STAGE_WARPS)
+    k_orient_stage(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
+                   double corner_thresh, unsigned char *__restrict__ ok,
+                   const OriTab *__restrict__ tabs, const float *__restrict__ pool, int pitch)
+{
+    extern __shared__ float4 s_rows4[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *tile = s_rows4 + (size_t)warp * 32 * pitch;
+    const int i = (blockIdx.x * ORI_STAGE_WARPS + warp) * 32 + lane;
+    const bool valid = i < n;
+    s3d_keypoint c;
+    c.o = 0, c.s = 0, c.x = c.y = c.z = 0.0f, c.sd = 1.0;
+    if (valid) c = kps[i];
+    const int lv = valid ? c.o * T.nlev_g + (c.s - T.first_level) : -1;
+    // one level for the whole warp?
+    const int lv0 = __shfl_sync(0xffffffffu, lv, 0);
+    const bool uniform = __all_sync(0xffffffffu, !valid || lv == lv0) && lv0 >= 0 && T.gptrs &&
+                         T.gptrs[lv0] != nullptr;
+    float R[9];
+    double conf = 0.0;
+    bool accept = false;
+    if (!uniform) {  // per-thread path (warp-uniform branch)
+        if (valid) {
+            const float zl = local_z(T, lv, c.z);
+            accept = orient_core_tab<4>(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1],
+                                        T.dims[3 * lv + 2], T.units[3 * lv], T.units[3 * lv + 1],
+                                        T.units[3 * lv + 2], (int)c.x, (int)c.y, (int)zl,
+                                        sig_fctr * c.sd, pool + tabs[lv].off, tabs[lv],
+                                        T.gptrs ? T.gptrs[lv] : nullptr, corner_thresh, R, conf);
+        }
+    } else {
+        const int L = lv0;
+        const OriTab t = tabs[L];
+        const int nx = T.dims[3 * L], ny = T.dims[3 * L + 1], nz = T.dims[3 * L + 2];
+        const float uxf = T.units[3 * L], uyf = T.units[3 * L + 1], uzf = T.units[3 * L + 2];
+        const float4 *__restrict__ gim = T.gptrs[L];
+        const float *__restrict__ tab = pool + t.off;
+        const long long nvox = (long long)nx * ny * nz;
+        const int cx = (int)c.x, cy = (int)c.y, cz = (int)local_z(T, L, c.z);
+        const double win_radius = sig_fctr * c.sd * 3.0;
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1, z0 = 0, z1 = -1;
+        if (valid) {  // bounds exactly as orient_core_tab
+            sphere_bounds_d((float)cx, win_radius, uxf, nx, x0, x1);
+            sphere_bounds_d((float)cy, win_radius, uyf, ny, y0, y1);
+            sphere_bounds_d((float)cz, win_radius, uzf, nz, z0, z1);
+            x0 = max(x0, cx - t.rx), x1 = min(x1, cx + t.rx);
+            y0 = max(y0, cy - t.ry), y1 = min(y1, cy + t.ry);
+            z0 = max(z0, cz - t.rz), z1 = min(z1, cz + t.rz);
+        }
+        const long long ys = nx, zs = (long long)nx * ny;
+        const int twx = 2 * t.rx + 1, twy = 2 * t.ry + 1;
+        double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+        float wx = 0.0f, wy = 0.0f, wz = 0.0f;
+        for (int dz = -t.rz; dz <= t.rz; dz++)
+            for (int dy = -t.ry; dy <= t.ry; dy++) {
+                const float *wr = tab + ((size_t)(dz + t.rz) * twy + (dy + t.ry)) * twx;
+                const float wreg = lane < twx ? __ldg(wr + lane) : -1.0f;
+                const unsigned inside = __ballot_sync(0xffffffffu, wreg >= 0.0f);
+                if (!inside) continue;  // the row misses the sphere (warp-uniform)
+                const int jlo = __ffs(inside) - 1, jhi = 31 - __clz(inside);
+                const int z = cz + dz, y = cy + dy;
+                const bool rowact = valid && z >= z0 && z <= z1 && y >= y0 && y <= y1;
+                const unsigned act = __ballot_sync(0xffffffffu, rowact);
+                if (!act) continue;
+                // voxel index of (cx - rx, y, z): the row this lane consumes
+                const long long ebase = (long long)z * zs + (long long)y * ys + (cx - t.rx);
+                for (unsigned m = act; m; m &= m - 1) {  // cooperative fetch, one row per step
+                    const int k = __ffs(m) - 1;
+                    const long long eb = __shfl_sync(0xffffffffu, ebase, k);
+                    if (lane >= jlo && lane <= jhi) {
+                        long long e = eb + lane;  // clamped: out-of-row voxels are never consumed
+                        e = e < 0 ? 0 : (e >= nvox ? nvox - 1 : e);
+                        tile[k * pitch + lane] = __ldg(gim + e);
+                    }
+                }
+                __syncwarp();
+                for (int j = jlo; j <= jhi; j++) {
+                    const float w = __shfl_sync(0xffffffffu, wreg, j);
+                    const int x = cx - t.rx + j;
+                    if (rowact && w >= 0.0f && x >= x0 && x <= x1) {
+                        const float4 g = tile[lane * pitch + j];
+                        const double dw = (double)w, gxd = g.x, gyd = g.y, gzd = g.z;
+                        a00 = __dadd_rn(a00, __dmul_rn(__dmul_rn(gxd, gxd), dw));
+                        a01 = __dadd_rn(a01, __dmul_rn(__dmul_rn(gxd, gyd), dw));
+                        a02 = __dadd_rn(a02, __dmul_rn(__dmul_rn(gxd, gzd), dw));
+                        a11 = __dadd_rn(a11, __dmul_rn(__dmul_rn(gyd, gyd), dw));
+                        a12 = __dadd_rn(a12, __dmul_rn(__dmul_rn(gyd, gzd), dw));
+                        a22 = __dadd_rn(a22, __dmul_rn(__dmul_rn(gzd, gzd), dw));
+                        wx = fa(wx, fm(g.x, w));
+                        wy = fa(wy, fm(g.y, w));
+                        wz = fa(wz, fm(g.z, w));
+                    }
+                }
+                __syncwarp();
+            }
+        if (valid)
+            accept = orient_finish(a00, a01, a02, a11, a12, a22, wx, wy, wz, corner_thresh, R, conf);
+    }
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) kps[i].R[k] = R[k];
+        ok[i] = accept ? 1 : 0;
+    }
+}
+
 // ordered compaction of accepted candidates (sift.c:1306-1324)
 __global__ void __launch_bounds__(1024)
     k_flag_scan(const unsigned char *__restrict__ ok, int n, int *__restrict__ pos,
@@ -1715,6 +1833,7 @@ static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr
     const int L = e->noct * e->nlev_g;
     std::vector<OriTab> tabs(L);
     size_t total = 0;
+    e->ori_max_twx = 0;
     for (int lv = 0; lv < L; lv++) {
         OriTab &t = tabs[lv];
         t.off = -1;
@@ -1729,6 +1848,7 @@ static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr
         t.rx = (int)ceil(r[0]) + 1;
         t.ry = (int)ceil(r[1]) + 1;
         t.rz = (int)ceil(r[2]) + 1;
+        e->ori_max_twx = std::max(e->ori_max_twx, 2 * t.rx + 1);
         const size_t n = (size_t)(2 * t.rx + 1) * (2 * t.ry + 1) * (2 * t.rz + 1);
         if (total + n > ((size_t)1 << 27)) return 1;
         t.off = (int)total;
@@ -1784,7 +1904,14 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
         const int trc = build_orient_tables(e, T, 1.5);
         if (trc < 0) return -1;
         if (trc == 0) {  // every keypoint level has a table
-            if (e->opt_orient_batch == 8)
+            const int pitch = e->ori_max_twx | 1;
+            const size_t stage_smem = (size_t)ORI_STAGE_WARPS * 32 * pitch * sizeof(float4);
+            if (e->opt_orient_stage && pitch <= 31 && stage_smem <= 48 * 1024)
+                k_orient_stage<<<(n + 32 * ORI_STAGE_WARPS - 1) / (32 * ORI_STAGE_WARPS),
+                                 32 * ORI_STAGE_WARPS, stage_smem, e->stream>>>(
+                    e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok,
+                    static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool, pitch);
+            else if (e->opt_orient_batch == 8)
                 k_orient<true, 8><<<(n + 127) / 128, 128, 0, e->stream>>>(
                     e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
                     static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool);
