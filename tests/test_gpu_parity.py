@@ -324,3 +324,33 @@ def test_descriptor_fixed_point_paths_agree(b200_lib):
                 assert np.array_equal(s.extract_descriptors()["hists"], base)
             finally:
                 cu.s3d_set_option(eng, b"desc_path", 0)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("S3D_EXPERIMENTAL") != "1",
+                    reason="experimental kernels are validated on request (S3D_EXPERIMENTAL=1)")
+def test_experimental_orient_stage_matches_default(b200_lib):
+    """`orient_stage` (the warp-cooperative orientation kernel, default off, written without
+    GPU time to measure it) must reproduce the default kernel's keypoints bit for bit -- same
+    accepted set, same order, same rotation matrices -- before anyone times it."""
+    from sift3d_b200 import capi
+    from sift3d_b200.volumes import blob_volume
+    cu = C.CDLL(str(capi.CUDA_LIB))
+    cu.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    b200_lib.lib.sift3d_b200_engine.restype = C.c_void_p
+    b200_lib.lib.sift3d_b200_engine.argtypes = [C.POINTER(capi.SIFT3D)]
+    rng = np.random.default_rng(11)
+    cases = [(blob_volume((72, 80, 96), seed=31), (1.0, 1.0, 1.0)),
+             (blob_volume((48, 52, 60), seed=23), (1.0, 1.3, 0.8)),
+             (rng.random((40, 44, 48), dtype=np.float32), (1.0, 1.0, 1.0))]
+    for vol, units in cases:
+        with capi.Sift3D(b200_lib) as s:
+            base = s.detect_keypoints(vol, units=units).copy()
+            eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+            try:
+                assert cu.s3d_set_option(eng, b"orient_stage", 1) == 0
+                kp = s.detect_keypoints(vol, units=units)
+                assert len(kp) == len(base)
+                for f in base.dtype.names:
+                    assert np.array_equal(kp[f], base[f]), f
+            finally:
+                cu.s3d_set_option(eng, b"orient_stage", 0)
