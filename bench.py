@@ -38,6 +38,7 @@ import numpy as np
 
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "oracle"))  # oracle_api: only the CPU-baseline legs use it
 
 METRIC = "voxels/sec through pyramid+descriptors"
 UNIT = "voxels/s"
@@ -152,8 +153,9 @@ def cpu_reference_run(n_sample, seed, threads=None):
     from sift3d_b200.volumes import blob_volume
     vol = blob_volume(n_sample, seed=seed)
     cores = threads or os.cpu_count()
-    if capi.REF_LIB.exists():
-        ref = capi.load_reference()
+    import oracle_api
+    if oracle_api.REF_LIB.exists():
+        ref = oracle_api.load_reference()
         with capi.Sift3D(ref) as s:
             t0 = time.perf_counter()
             kp = s.detect_keypoints(vol)
@@ -163,7 +165,7 @@ def cpu_reference_run(n_sample, seed, threads=None):
             t2 = time.perf_counter()
         kind = "reference"
     else:
-        from sift3d_b200.oracle_api import Oracle
+        from oracle_api import Oracle
         orc = Oracle()
         t0 = time.perf_counter()
         kp = orc.detect(vol)

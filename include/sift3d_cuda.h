@@ -93,6 +93,10 @@ int s3d_detect_extrema(s3d_engine *e, double peak_thresh, int *num_candidates);
 /* assign_orientations (sift.c:1264): rejects + stable compaction. */
 int s3d_assign_orientations(s3d_engine *e, double corner_thresh, int *num_keypoints);
 int s3d_candidates_download(s3d_engine *e, s3d_keypoint *out, int cap);
+/* Counts left by the last s3d_detect_extrema / s3d_assign_orientations (num in detect_extrema,
+ * sift.c:1197; kp->slab.num after assign_orientations, sift.c:1306-1324). */
+int s3d_num_candidates(const s3d_engine *e);
+int s3d_num_keypoints(const s3d_engine *e);
 int s3d_keypoints_download(s3d_engine *e, s3d_keypoint *out, int cap);
 
 /* _SIFT3D_extract_descriptors (sift.c:2207) on the resident Gaussian pyramid.

@@ -1,8 +1,10 @@
-"""ctypes access to oracle/_build/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+"""ctypes access to oracle/_build/liboracle.so (the CPU restatement) and to the compiled
+reference in oracle/_ref -- TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs import this module.  The product path (sift3d_b200.capi -> libsift3D.so ->
-libsift3d_cuda.so) never does.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module (`sys.path` gets the `oracle/` directory there).  Nothing under
+sift3d_b200/ imports it; the product path is sift3d_b200.capi -> libsift3D.so ->
+libsift3d_cuda.so and fails loudly without a CUDA device.
 """
 from __future__ import annotations
 
@@ -13,6 +15,18 @@ import numpy as np
 
 REPO = Path(__file__).resolve().parent.parent
 ORACLE_LIB = REPO / "oracle" / "_build" / "liboracle.so"
+REF_DIR = REPO / "oracle" / "_ref"
+REF_LIB = REF_DIR / "libsift3D_ref.so"
+REF_IMUTIL = REF_DIR / "libimutil_ref.so"
+
+
+def load_reference():
+    """The UNMODIFIED reference compiled by oracle/build_ref.sh, behind the same ctypes
+    wrapper class the product library uses (byte-identical struct layouts)."""
+    import sys
+    sys.path.insert(0, str(REPO))
+    from sift3d_b200 import capi
+    return capi.Sift3DLib(REF_LIB, "reference")
 
 
 class OrcParams(C.Structure):

@@ -7,8 +7,8 @@ names and argument meaning (`sift3d/sift.h:19-108`).  Because the layouts are
 byte-identical, ONE wrapper class drives either
 
   * the B200 library built from this repo (`sift3d_b200/lib/libsift3D.so`), or
-  * the unmodified reference compiled into `oracle/_ref/libsift3D_ref.so`
-    (test infrastructure; only tests/bench/smoke load it),
+  * any other build of the same ABI -- the tests hand it the unmodified reference
+    (`oracle/oracle_api.py:load_reference`, test infrastructure outside this package),
 
 which is what makes the parity tests read like "same calls, two libraries".
 
@@ -27,9 +27,6 @@ REPO = Path(__file__).resolve().parent.parent
 LIB_DIR = Path(__file__).resolve().parent / "lib"
 B200_LIB = LIB_DIR / "libsift3D.so"
 CUDA_LIB = LIB_DIR / "libsift3d_cuda.so"
-REF_DIR = REPO / "oracle" / "_ref"
-REF_LIB = REF_DIR / "libsift3D_ref.so"
-REF_IMUTIL = REF_DIR / "libimutil_ref.so"
 
 NHIST_PER_DIM = 4
 ICOS_NVERT = 12
@@ -409,8 +406,3 @@ def im_resample(lib: Sift3DLib, vol: np.ndarray, units_in, units_out, interp: in
 
 def load_b200() -> Sift3DLib:
     return Sift3DLib(B200_LIB, "b200")
-
-
-def load_reference() -> Sift3DLib:
-    """The unmodified reference compiled by oracle/build_ref.sh (TEST/BENCH ONLY)."""
-    return Sift3DLib(REF_LIB, "reference")

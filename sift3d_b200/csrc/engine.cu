@@ -524,6 +524,8 @@ int s3d_candidates_download(s3d_engine *e, s3d_keypoint *out, int cap)
 }
 
 const s3d_keypoint *s3d_device_keypoints(const s3d_engine *e) { return e->d_kp; }
+int s3d_num_candidates(const s3d_engine *e) { return e->ncand; }
+int s3d_num_keypoints(const s3d_engine *e) { return e->nkp; }
 
 int s3d_extract_descriptors_device(s3d_engine *e, const s3d_keypoint *dev_kp, int n,
                                    void *dev_desc)

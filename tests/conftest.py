@@ -8,6 +8,7 @@ import pytest
 
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "oracle"))  # oracle_api: test infrastructure, outside the package
 GOLDEN = REPO / "tests" / "golden"
 
 
@@ -45,16 +46,16 @@ def built():
 
 @pytest.fixture(scope="session")
 def oracle_cls(built):
-    from sift3d_b200.oracle_api import Oracle
+    from oracle_api import Oracle
     return Oracle
 
 
 @pytest.fixture(scope="session")
 def ref_lib(built):
-    from sift3d_b200 import capi
-    if not capi.REF_LIB.exists():
+    import oracle_api
+    if not oracle_api.REF_LIB.exists():
         pytest.skip("oracle/_ref not built (needs /root/reference)")
-    return capi.load_reference()
+    return oracle_api.load_reference()
 
 
 @pytest.fixture(scope="session")

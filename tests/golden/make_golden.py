@@ -20,6 +20,8 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent.parent))
+sys.path.insert(0, str(HERE.parent.parent / "oracle"))
+import oracle_api  # noqa: E402
 from sift3d_b200 import capi  # noqa: E402
 from sift3d_b200.volumes import blob_volume, smooth_noise_volume  # noqa: E402
 
@@ -95,8 +97,84 @@ def run_dense_rotate(ref):
     np.savez_compressed(HERE / "dense_rotate.npz", **out)
 
 
+def candidate_count(prev, cur, nxt, peak_thresh):
+    """numpy restatement of detect_extrema's test (sift3d/sift.c:1153-1208) on one DoG triple:
+    strict 6 face neighbours + the same voxel one level below and above, |v| > f32(peak*dogmax)."""
+    dogmax = np.float32(np.abs(cur).max())
+    thr = np.float32(np.float64(peak_thresh) * np.float64(dogmax))
+    c = cur[1:-1, 1:-1, 1:-1]
+    nb = [cur[1:-1, 1:-1, 2:], cur[1:-1, 1:-1, :-2], cur[1:-1, 2:, 1:-1], cur[1:-1, :-2, 1:-1],
+          cur[:-2, 1:-1, 1:-1], cur[2:, 1:-1, 1:-1], prev[1:-1, 1:-1, 1:-1], nxt[1:-1, 1:-1, 1:-1]]
+    lo = np.ones(c.shape, bool)
+    hi = np.ones(c.shape, bool)
+    for n in nb:
+        lo &= n > c
+        hi &= n < c
+    return int((((c > thr) | (c < -thr)) & (lo | hi)).sum())
+
+
+def run_large(ref, n, seed=1234, desc_every=25, with_dense=False):
+    """BASELINE.json configs[1] (n = 512) / the configs[2] volume (n = 256): the exact volume
+    bench.py times, through the UNMODIFIED reference.  Stores digests of every pyramid level,
+    the candidate count, the full keypoint table and every `desc_every`-th descriptor."""
+    import time
+    t0 = time.time()
+    vol = blob_volume(n, seed=seed)
+    out = {"n": np.int32(n), "seed": np.int32(seed), "input_sha256": np.asarray(level_digest(vol)),
+           "desc_every": np.int32(desc_every),
+           "units": np.ones(3), "params": np.asarray([0.1, 0.4, 1.15, 1.6, 3], np.float64)}
+    print(f"blob{n}: volume in {time.time() - t0:.0f} s", flush=True)
+    with capi.Sift3D(ref) as s:
+        t0 = time.time()
+        kp = s.detect_keypoints(vol)
+        out["ref_detect_s"] = np.float64(time.time() - t0)
+        out["noct"] = np.int32(s.num_octaves())
+        digs, ncand = [], []
+        for o in range(s.num_octaves()):
+            for lv in range(-1, 5):
+                digs.append(f"g,{o},{lv}," + level_digest(s.level_data("gpyr", o, lv)))
+            dog = [s.level_data("dog", o, lv) for lv in range(-1, 4)]
+            for lv in range(-1, 4):
+                digs.append(f"d,{o},{lv}," + level_digest(dog[lv + 1]))
+            for lv in range(0, 3):
+                ncand.append(candidate_count(dog[lv], dog[lv + 1], dog[lv + 2], 0.1))
+            del dog
+        out["level_sha256"] = np.asarray(digs)
+        out["candidates_per_level"] = np.asarray(ncand, np.int64)
+        out["kp_xyz"] = np.stack([kp["xd"], kp["yd"], kp["zd"]], 1).astype(np.int16)
+        assert np.array_equal(out["kp_xyz"].astype(np.float64),
+                              np.stack([kp["xd"], kp["yd"], kp["zd"]], 1))
+        out["kp_o"] = kp["o"].astype(np.int8)
+        out["kp_s"] = kp["s"].astype(np.int8)
+        out["kp_sd"] = kp["sd"]
+        out["kp_R"] = kp["R"]
+        t0 = time.time()
+        d = s.extract_descriptors()
+        out["ref_describe_s"] = np.float64(time.time() - t0)
+        out["desc"] = d["hists"][::desc_every].astype(np.float32)
+        out["desc_norm_sum"] = np.float64(np.linalg.norm(d["hists"].astype(np.float64), axis=1).sum())
+        print(f"blob{n}: octaves={int(out['noct'])} candidates={int(sum(ncand))} keypoints={len(kp)} "
+              f"detect {float(out['ref_detect_s']):.0f} s describe {float(out['ref_describe_s']):.0f} s",
+              flush=True)
+        if with_dense:
+            t0 = time.time()
+            dd = s.extract_dense_descriptors(vol)
+            out["ref_dense_s"] = np.float64(time.time() - t0)
+            out["dense_sub"] = dd[3::8, 3::8, 3::8].copy()
+            out["dense_plane_sums"] = dd.astype(np.float64).sum(axis=(1, 2))
+            out["dense_plane"] = dd[n // 2, ::2, ::2].copy()
+            print(f"blob{n}: dense {float(out['ref_dense_s']):.0f} s", flush=True)
+    np.savez_compressed(HERE / f"blob{n}_large.npz", **out)
+
+
 def main():
-    ref = capi.load_reference()
+    ref = oracle_api.load_reference()
+    if "--large" in sys.argv:
+        # run once in the build container (about 2 + 8 minutes of CPU on 8 cores)
+        sizes = [int(a) for a in sys.argv[sys.argv.index("--large") + 1:]] or [256, 512]
+        for n in sizes:
+            run_large(ref, n, desc_every=10 if n <= 256 else 50, with_dense=(n == 256))
+        return
     if "--dense-rotate-only" in sys.argv:
         run_dense_rotate(ref)
         return

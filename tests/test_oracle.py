@@ -148,11 +148,11 @@ def test_mesh_quirk(oracle_cls):
 
 # ---------------------------------------------------------------- SURVEY.md 8f rows N1 / N3
 def _ref_imutil():
-    from sift3d_b200 import capi
-    if not capi.REF_IMUTIL.exists():
+    import oracle_api
+    if not oracle_api.REF_IMUTIL.exists():
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     import ctypes as C
-    return C.CDLL(str(capi.REF_IMUTIL))
+    return C.CDLL(str(oracle_api.REF_IMUTIL))
 
 
 def _ref_inv_transform(L, vol, A, out_shape, interp):

@@ -5,7 +5,8 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from sift3d_b200.engine_api import Engine
-from sift3d_b200.oracle_api import Oracle
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent / 'oracle'))
+from oracle_api import Oracle
 from bench import gauss_taps, pyramid_filters
 e = Engine(0)
 e.L.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]

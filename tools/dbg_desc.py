@@ -3,7 +3,8 @@ from pathlib import Path
 import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from sift3d_b200 import capi
-from sift3d_b200.oracle_api import Oracle
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent / 'oracle'))
+from oracle_api import Oracle
 from sift3d_b200.volumes import noise_volume
 vol = noise_volume((40, 48, 56), 1)
 lib = capi.load_b200(); orc = Oracle()

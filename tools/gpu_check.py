@@ -11,7 +11,8 @@ REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 from sift3d_b200 import capi  # noqa: E402
 from sift3d_b200.engine_api import Engine  # noqa: E402
-from sift3d_b200.oracle_api import Oracle  # noqa: E402
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent / 'oracle'))
+from oracle_api import Oracle  # noqa: E402
 from sift3d_b200.volumes import blob_volume, noise_volume  # noqa: E402
 
 
