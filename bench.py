@@ -249,6 +249,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=160, help="edge of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blur-reps", type=int, default=5)
+    ap.add_argument("--opt", action="append", default=[],
+                    help="engine option name=value for A/B runs (s3d_set_option), repeatable")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -313,6 +315,11 @@ def main():
     nkp, d2h = e2e_step()
     eng = lib.lib.sift3d_b200_engine(C.byref(s.s))
     cu.s3d_engine_set_stream(eng, C.c_void_p(stream.cuda_stream))
+    cu.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    for kv in args.opt:
+        k, v = kv.split("=")
+        if cu.s3d_set_option(eng, k.encode(), int(v)) != 0:
+            raise SystemExit(f"unknown engine option {k}")
     desc_dev = torch.empty(max(nkp, 1) * 3104 + 4096, dtype=torch.uint8, device=dev)
 
     def dev_step():

@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -74,6 +75,7 @@ struct s3d_engine {
     int blur_mode = 0;
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
+    int opt_desc_v2 = 0;  // 1: k_descriptor2 (raster-order rows) instead of k_descriptor3 (cell-owner lanes)
     int opt_orient_stage = 0;  // 1: k_orient_stage (experimental, unmeasured) instead of k_orient
     int ori_max_twx = 0;       // widest weight-table row of the current orientation tables
     int opt_orient_batch = 4;  // voxels k_orient fetches ahead (4, or 8 = line-aligned batches)
@@ -206,13 +208,27 @@ int s3d_ensure_scratch(s3d_engine *e, size_t elems);
 int s3d_k_orientations(s3d_engine *e, double corner_thresh);
 int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
                       double corner_thresh, unsigned char *d_ok, double *d_conf);
-int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out);
+// kp_levels_only: every keypoint sits on a keypoint level s = 0..K-1 of the resident pyramid and
+// its window passes s3d_desc_window_fine (then the cell-owner kernel k_descriptor3 is used)
+int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out,
+                      int kp_levels_only);
 int s3d_k_dense(s3d_engine *e, const float *d_smooth, const float *d_raw, int nx, int ny, int nz,
                 const float inv_units[3], float *d_temp12);
 int s3d_k_dense_rotate(s3d_engine *e, const float *d_smooth, int nx, int ny, int nz,
                        const float units[3], double ori_sigma, double desc_sigma,
                        double corner_thresh, float *d_out12);
 int s3d_k_dense_post(s3d_engine *e, float *d_desc12, const float *d_raw, size_t nvox);
+// Whether the one-word fixed-point histogram of k_descriptor3 keeps >= 18 bits below the largest
+// gradient of the window for a keypoint of scale sd on a level with these units: the sum of the
+// trilinear weights of a bin (hist_width + voxel diagonal)^3 / voxel volume, hist_width = 5 sd
+// (sift.c:1845-1850), must stay below 8192 voxels.  Larger windows (user keypoints at coarse
+// scales on a fine level) take k_descriptor2 with its two-word bins.
+inline bool s3d_desc_window_fine(double sd, double ux, double uy, double uz)
+{
+    const double hw = sd * 7.071067812 * 2.0 / 1.4142135623730951 / 2.0;
+    const double side = hw + sqrt(ux * ux + uy * uy + uz * uz);
+    return side * side * side / (ux * uy * uz) <= 8192.0;
+}
 int s3d_upload_mesh(s3d_engine *e, const float *v, const int *idx);
 int s3d_gradients_prepare(s3d_engine *e);  // best effort: 0 also when memory is short
 void s3d_gradients_free(s3d_engine *e);

@@ -105,57 +105,89 @@ __host__ __device__ inline void d3_cell_bbox(const D3Key &K, int i0, int i1, int
     C.zhi = zhi < K.z1 ? zhi : K.z1;
 }
 
+// Row-scan constants of a keypoint (block-uniform; the kernel keeps them in shared memory).
+struct D3Scan {
+    float kx, ky, kz, uy, uz, iux;
+    float r2w;             // r2 * (1 + 2e-5)
+    float b1[3], b2[3];    // Rt[3a + 1] * binf, Rt[3a + 2] * binf
+    float hb;              // half * binf
+    float isl[3];
+    int flat;
+    int x0, x1;
+};
+
+__host__ __device__ inline void d3_scan_setup(const D3Key &K, D3Scan &Q)
+{
+    Q.kx = K.kx, Q.ky = K.ky, Q.kz = K.kz, Q.uy = K.uy, Q.uz = K.uz, Q.iux = 1.0f / K.ux;
+    Q.r2w = K.r2 + 2e-5f * K.r2;
+    for (int a = 0; a < 3; a++) {
+        Q.b1[a] = K.Rt[3 * a + 1] * K.binf;
+        Q.b2[a] = K.Rt[3 * a + 2] * K.binf;
+        Q.isl[a] = K.isl[a];
+    }
+    Q.hb = K.half * K.binf;
+    Q.flat = K.flat;
+    Q.x0 = K.x0, Q.x1 = K.x1;
+}
+
 // x interval [xa, xa + cnt) of row (y, z) containing every voxel of the cell inside the sphere.
 // Approximate arithmetic: the sphere chord is widened by 2e-5 * r2 under the root (its rounding
 // error is about 4 ulp of r2 and the root magnifies it near tangent rows), the slab ends by
 // 0.01 voxel (their error is below 3e-3 voxel for |Rt[3a]| >= 0.01: an ulp of vb divided by the
-// slope), and a slab with |Rt[3a]| < 0.01 (vb_a then varies by less than 2.83 * 0.01 bins along a row:
-// bin_fctr * win_radius = 2 sqrt 2) only rejects rows that miss it by more than 0.04 bin.
-__host__ __device__ inline void d3_scan_row(const D3Key &K, const D3Cell &C, int y, int z, int &xa, int &cnt)
+// slope), and a slab with |Rt[3a]| < 0.01 (vb_a then varies by less than 2.83 * 0.01 bins along a
+// row: bin_fctr * win_radius = 2 sqrt 2) only rejects rows that miss it by more than 0.04 bin.
+__host__ __device__ __forceinline__ void d3_scan_row(const D3Scan &Q, const float ibf[3], int y, int z,
+                                                     int &xa, int &cnt)
 {
     cnt = 0;
     xa = 0;
-    const float vy = ((float)y - K.ky) * K.uy, vz = ((float)z - K.kz) * K.uz;
-    const float rem = K.r2 - (vy * vy + vz * vz) + 2e-5f * K.r2;
+    const float vy = ((float)y - Q.ky) * Q.uy, vz = ((float)z - Q.kz) * Q.uz;
+    const float rem = Q.r2w - fmaf(vy, vy, vz * vz);
     if (rem < 0.0f) return;
-    const float hx = sqrtf(rem) / K.ux;
+#ifdef __CUDA_ARCH__
+    const float hx = rem * rsqrtf(fmaxf(rem, 1e-30f)) * Q.iux;  // 2 ulp: far inside the widening
+#else
+    const float hx = sqrtf(rem) * Q.iux;
+#endif
     float lo = -hx, hi = hx;
+#pragma unroll
     for (int a = 0; a < 3; a++) {
-        const float off = (K.Rt[3 * a + 1] * vy + K.Rt[3 * a + 2] * vz + K.half) * K.binf - C.ibf[a];
-        if (K.flat & (1 << a)) {
+        const float off = fmaf(Q.b1[a], vy, fmaf(Q.b2[a], vz, Q.hb)) - ibf[a];
+        if (Q.flat & (1 << a)) {
             if (off < -0.04f || off > 1.04f) return;
         } else {
-            const float t0 = -off * K.isl[a], t1 = (1.0f - off) * K.isl[a];
+            const float t0 = -off * Q.isl[a], t1 = t0 + Q.isl[a];
             lo = fmaxf(lo, fminf(t0, t1));
             hi = fminf(hi, fmaxf(t0, t1));
         }
     }
     if (!(lo <= hi + 0.02f)) return;
-    int a0 = (int)ceilf(K.kx + lo - 0.01f), b0 = (int)floorf(K.kx + hi + 0.01f);
-    if (a0 < K.x0) a0 = K.x0;
-    if (b0 > K.x1) b0 = K.x1;
+    int a0 = (int)ceilf(Q.kx + lo - 0.01f), b0 = (int)floorf(Q.kx + hi + 0.01f);
+    if (a0 < Q.x0) a0 = Q.x0;
+    if (b0 > Q.x1) b0 = Q.x1;
     if (b0 < a0) return;
     xa = a0;
     cnt = b0 - a0 + 1;
 }
 
 // The exact per-voxel geometry (sift.c:1866-1881, 1700-1716): squared distance, the three bin
-// coordinates, and whether the reference visits the voxel AND its base cell is C.  dv = vb - ib
+// coordinates, and whether the reference visits the voxel AND its base cell is ibf.  dv = vb - ib
 // is exact for vb in [ib, ib + 1) (Sterbenz), so `dv >= 0 && dv < 1` is floor(vb) == ib.
-__host__ __device__ inline bool d3_member(const D3Key &K, const D3Cell &C, float xf, float yf, float zf,
-                                          float &sq, float dv[3])
+// (r2 is passed separately: the kernel reads it back from shared memory, see k_descriptor2.)
+__host__ __device__ __forceinline__ bool d3_member(const D3Key &K, const float ibf[3], float r2, float xf,
+                                                   float yf, float zf, float &sq, float dv[3])
 {
     const float vx = D3_MUL(D3_SUB(xf, K.kx), K.ux);
     const float vy = D3_MUL(D3_SUB(yf, K.ky), K.uy);
     const float vz = D3_MUL(D3_SUB(zf, K.kz), K.uz);
     sq = D3_ADD(D3_ADD(D3_MUL(vx, vx), D3_MUL(vy, vy)), D3_MUL(vz, vz));
-    bool ok = !(sq > K.r2);
+    bool ok = !(sq > r2);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         const float vk = D3_ADD(D3_ADD(D3_MUL(K.Rt[3 * a], vx), D3_MUL(K.Rt[3 * a + 1], vy)),
                                 D3_MUL(K.Rt[3 * a + 2], vz));
         const float vb = D3_MUL(D3_ADD(vk, K.half), K.binf);
-        dv[a] = D3_SUB(vb, C.ibf[a]);
+        dv[a] = D3_SUB(vb, ibf[a]);
         ok = ok && dv[a] >= 0.0f && dv[a] < 1.0f;
     }
     return ok;

@@ -233,6 +233,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     if (!strcmp(name, "icos_fast")) e->opt_icos_fast = value;
     else if (!strcmp(name, "blur_mode")) e->blur_mode = value;
     else if (!strcmp(name, "desc_v1")) e->opt_desc_v1 = value;
+    else if (!strcmp(name, "desc_v2")) e->opt_desc_v2 = value;
     else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 7;
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
     else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
@@ -533,7 +534,15 @@ int s3d_extract_descriptors_device(s3d_engine *e, const s3d_keypoint *dev_kp, in
     DeviceGuard guard(e->device);
     if (e->noct < 1)
         return s3d_fail(e, "s3d_extract_descriptors: no pyramid", cudaSuccess, __FILE__, __LINE__);
-    return s3d_k_descriptors(e, dev_kp, n, (unsigned char *)dev_desc);
+    // device-resident keypoints come from s3d_assign_orientations: keypoint levels only, at
+    // the scale of their level
+    int fine = dev_kp == e->d_kp;
+    for (int lv = 0; fine && lv < (int)e->g.size(); lv++) {
+        const int sidx = lv % e->nlev_g + e->first_level;
+        const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
+        if (sidx >= 0 && sidx < e->K && !s3d_desc_window_fine(g.scale, g.ux, g.uy, g.uz)) fine = 0;
+    }
+    return s3d_k_descriptors(e, dev_kp, n, (unsigned char *)dev_desc, fine);
 }
 
 int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *host_desc)
@@ -542,11 +551,19 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
     if (n < 1) return s3d_fail(e, "s3d_extract_descriptors: n < 1", cudaSuccess, __FILE__, __LINE__);
     if (e->noct < 1)
         return s3d_fail(e, "s3d_extract_descriptors: no pyramid", cudaSuccess, __FILE__, __LINE__);
-    for (int i = 0; i < n; i++)
+    int kp_levels_only = 1;  // every keypoint on a level s = 0..K-1 (those have gradient volumes)
+    for (int i = 0; i < n; i++) {
         if (kp[i].o < 0 || kp[i].o >= e->noct || kp[i].s < e->first_level ||
             kp[i].s > e->first_level + e->nlev_g - 1)
             return s3d_fail(e, "s3d_extract_descriptors: keypoint octave/level outside the pyramid",
                             cudaSuccess, __FILE__, __LINE__);
+        if (kp[i].s < 0 || kp[i].s >= e->K) kp_levels_only = 0;
+        if (kp_levels_only) {
+            const size_t lv = (size_t)kp[i].o * e->nlev_g + (kp[i].s - e->first_level);
+            const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
+            if (!s3d_desc_window_fine(kp[i].sd, g.ux, g.uy, g.uz)) kp_levels_only = 0;
+        }
+    }
     if (n > e->kp_in_cap) {
         if (e->d_kp_in) cudaFree(e->d_kp_in);
         e->d_kp_in = nullptr;
@@ -576,7 +593,8 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
     int rc = 0;
     for (int c = 0; c < nchunks && !rc; c++) {
         const int lo = c * chunk, cnt = std::min(chunk, n - lo);
-        rc = s3d_k_descriptors(e, e->d_kp_in + lo, cnt, e->d_desc + (size_t)lo * S3D_DESC_STRIDE);
+        rc = s3d_k_descriptors(e, e->d_kp_in + lo, cnt, e->d_desc + (size_t)lo * S3D_DESC_STRIDE,
+                               kp_levels_only);
         if (rc) break;
         if (cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventRecord(done[c], e->stream) != cudaSuccess)

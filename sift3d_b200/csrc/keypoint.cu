@@ -11,6 +11,7 @@
 // the ORDER of histogram accumulation differs (parallel), which costs ~1e-7
 // relative L2 against a 1e-4 budget.
 #include "common.cuh"
+#include "desc_cell_geom.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -1479,6 +1480,347 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
     }
 }
 
+// ---------------------------------------------------------------- sparse descriptor, version 3
+// "Cell-owner lanes" (the default).  One CTA (8 warps) per keypoint as before, but the window is
+// enumerated BY BASE CELL of the 4x4x4 descriptor grid instead of in raster order
+// (desc_cell_geom.cuh): lane l of a warp owns the base cell (l & 3, (l >> 2) & 3,
+// 2 * (warp & 1) + (l >> 4)) for the whole kernel and walks the voxels whose bin coordinate
+// vb = (R^T v + half) * bin_fctr has floor(vb) equal to that cell; warp w takes the rows
+// r = (w >> 1) (mod 4) of every cell's bounding box.  Consequences:
+//   * the 32 lanes of a warp scatter into 32 DIFFERENT cells at every instruction.  The
+//     histogram is stored vertex-major, h[vertex][cell] with cell (ix, iy, iz) of the padded
+//     5x5x5 grid at word ix + 8 iy + 68 iz and 352 (= 0 mod 32) words per vertex plane, so the
+//     bank of an update is (ix + 8 iy + 4 iz + corner offset) mod 32 whatever its vertex:
+//     the 32 lanes hit 32 different banks -- one shared-memory wavefront per atomic instead of
+//     the 3.6 of lanes that sit in random cells (k_descriptor2, ncu);
+//   * floor(vb) is a lane constant: no floorf / F2I / cell address arithmetic per voxel, the
+//     trilinear fractions are vb - ib, and the eight corner addresses are the lane's cell
+//     address plus compile-time offsets;
+//   * no carry logic: the histogram is one u32 per bin.  The fixed-point scale 2^S is chosen
+//     per keypoint from a BOUND on the gradient magnitude inside the window (maxima over
+//     8x8x1 voxel blocks, written by k_gradient next to the gradient volume) and on the number
+//     of voxels in a bin's support, so that a bin cannot overflow; contributions keep >= 17
+//     bits below the window's largest gradient (rounding noise of a bin ~1e-6 relative, against
+//     the 1e-4 budget), and integer accumulation stays order-independent: descriptors are
+//     bit-reproducible and identical between whole-volume and Z-slab-tiled runs (the block
+//     maxima are per plane, so both see the same bound).
+// Rows are found by a per-lane scan (d3_scan_row: ~60 instructions per row, a superset
+// interval) done in rounds of four rows whenever some lane runs dry; the intervals wait in a
+// small per-lane ring in shared memory, so lanes with short and long rows stay busy together.
+// Every voxel passes the exact test (d3_member) before it is used.
+#define D3_THREADS 256
+#define D3_VSTRIDE 352
+#define D3_RING 8
+struct D3Smem {
+    unsigned h[12 * D3_VSTRIDE];
+    unsigned long long tab[32];
+    FaceConst face[20];  // idx[] rewritten to byte offsets of the vertex planes
+    int lut[32];
+    float kc[4];  // r2, s2
+    D3Scan scan;  // row-scan constants of the keypoint
+    int4 cur[D3_THREADS];  // per-lane scan cursor {next row, rows in the bounding box, BY, ylo | zlo << 16}
+    uint2 ring[D3_THREADS / 32][D3_RING][32];  // per-lane queue of scanned rows {xa | cnt << 16, y | z << 16}
+};
+
+template <int OFF>
+__device__ __forceinline__ void red_add_off(unsigned addr, unsigned v)
+{
+    asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u2(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u2(unsigned addr, unsigned x, unsigned y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+// 1.5 * 2^23: fma(a, b, MAGIC) holds round(a * b) in its low mantissa bits for |a * b| < 2^22
+#define D3_MAGIC 12582912.0f
+#define D3_MAGIC_BITS 0x4B400000u
+
+template <int OCC, bool FAST>
+__global__ void __launch_bounds__(D3_THREADS, OCC)
+    k_descriptor3(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
+                  const MeshDev *__restrict__ M, unsigned char *__restrict__ out)
+{
+    __shared__ D3Smem S;
+    __shared__ float hist[S3D_DESC_NUMEL];
+    __shared__ double s_red[D3_THREADS / 32];
+    __shared__ float s_norm_inv;
+    __shared__ float s_gmax[D3_THREADS / 32];
+    unsigned sb = (unsigned)__cvta_generic_to_shared(&S);
+    asm volatile("" : "+r"(sb));  // opaque: one base register for all shared data (see k_descriptor2)
+    const unsigned h_addr = sb + (unsigned)offsetof(D3Smem, h);
+    const FaceSh faces{sb + (unsigned)offsetof(D3Smem, face), sb + (unsigned)offsetof(D3Smem, lut)};
+    const TabSh etab{sb + (unsigned)offsetof(D3Smem, tab)};
+    const unsigned kc_addr = sb + (unsigned)offsetof(D3Smem, kc);
+    const int ki = blockIdx.x;
+    if (ki >= n) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    s3d_keypoint kp = kps[ki];
+    const int lv = kp.o * T.nlev_g + (kp.s - T.first_level);
+    const float z_global = kp.z;
+    kp.z = local_z(T, lv, kp.z);
+    const float4 *__restrict__ gim = T.gptrs ? T.gptrs[lv] : nullptr;
+    if (gim == nullptr) __trap();  // the launcher only picks this kernel for levels with gradient volumes
+    const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
+    const float uxf = T.units[3 * lv], uyf = T.units[3 * lv + 1], uzf = T.units[3 * lv + 2];
+    const float iux = __fdiv_rn(1.0f, uxf), iuy = __fdiv_rn(1.0f, uyf), iuz = __fdiv_rn(1.0f, uzf);
+    const float sigma = (float)__dmul_rn(kp.sd, 7.071067812);  // sift.c:1845-1850
+    const float win_radius = (float)__dmul_rn(2.0, (double)sigma);
+    D3Key K;
+    K.kx = kp.x, K.ky = kp.y, K.kz = kp.z;
+    K.ux = uxf, K.uy = uyf, K.uz = uzf;
+    K.half = (float)__ddiv_rn((double)win_radius, sqrt(2.0));
+    const float desc_width = fm(2.0f, K.half);
+    K.hw = __fdiv_rn(desc_width, 4.0f);
+    K.binf = __fdiv_rn(1.0f, K.hw);
+    K.r2 = fm(win_radius, win_radius);
+    const float s2 = fm(sigma, sigma);
+    sphere_bounds_f(kp.x, win_radius, uxf, nx, K.x0, K.x1);
+    sphere_bounds_f(kp.y, win_radius, uyf, ny, K.y0, K.y1);
+    sphere_bounds_f(kp.z, win_radius, uzf, nz, K.z0, K.z1);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) K.Rt[3 * i + j] = kp.R[3 * j + i];
+    d3_key_finish(K);
+
+    for (int i = tid; i < 12 * D3_VSTRIDE; i += D3_THREADS) S.h[i] = 0;
+    if (tid < 32) S.tab[tid] = c_exp2f_tab[tid];
+    if (tid == 0) {
+        S.kc[0] = K.r2, S.kc[1] = s2;
+        d3_scan_setup(K, S.scan);
+    }
+    load_faces(S.face, S.lut, M);
+    // Bound of the gradient magnitude over the window's bounding box, from the per-plane 8x8
+    // block maxima of |g|^2 behind the gradient volume.
+    float m2 = 0.0f;
+    {
+        const int nbx = (nx + 7) >> 3, nby = (ny + 7) >> 3;
+        const float *__restrict__ bm = reinterpret_cast<const float *>(gim + (size_t)nx * ny * nz);
+        const int bx0 = K.x0 >> 3, by0 = K.y0 >> 3;
+        const int wbx = (K.x1 >> 3) - bx0 + 1, wby = (K.y1 >> 3) - by0 + 1, wz = K.z1 - K.z0 + 1;
+        const int tot = wbx > 0 && wby > 0 && wz > 0 ? wbx * wby * wz : 0;
+        for (int t = tid; t < tot; t += D3_THREADS) {
+            const int bxi = t % wbx, r = t / wbx;
+            const int byi = r % wby, zi = r / wby;
+            m2 = fmaxf(m2, __ldg(bm + ((size_t)(K.z0 + zi) * nby + by0 + byi) * nbx + bx0 + bxi));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        if (lane == 0) s_gmax[warp] = m2;
+    }
+    // ---- this lane's cell and its rows ---------------------------------------------------
+    const int ib0 = lane & 3, ib1 = (lane >> 2) & 3, ib2 = 2 * (warp & 1) + (lane >> 4);
+    bool scan_done;
+    {
+        D3Cell Cc;
+        d3_cell_bbox(K, ib0, ib1, ib2, Cc);
+        const int BY = Cc.yhi - Cc.ylo + 1, BZ = Cc.zhi - Cc.zlo + 1;
+        const int nrows = BY > 0 && BZ > 0 ? BY * BZ : 0;
+        // rows (warp >> 1) + 4k of the bounding box, in (z, y) order
+        S.cur[tid] = make_int4(warp >> 1, nrows, max(BY, 1), max(Cc.ylo, 0) | (max(Cc.zlo, 0) << 16));
+        scan_done = (warp >> 1) >= nrows;
+    }
+    __syncthreads();
+    if (tid < 60) {  // vertex index -> byte offset of its plane
+        int *w = &S.face[tid / 3].idx[tid % 3];
+        *w = *w * (D3_VSTRIDE * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < D3_THREADS / 32; i++) m2 = fmaxf(m2, s_gmax[i]);
+    // Fixed-point scale 2^S (block-uniform).  A contribution is mag * 2^S * w_c * bary with
+    // mag <= gmax * 1.001 (window weight <= 1; the rotation keeps the norm to 1e-6),
+    // bary <= 1 + 2 bary_eps and w_c the trilinear weight of the voxel for the bin's cell,
+    // a product of three hat functions of the rotated coordinate.  Summed over the voxel
+    // lattice, sum_v w_c(v) <= integral of sup_{|y - x| <= D/2} w_c(y) dx / voxel volume
+    // <= hist_width^3 * (1 + 2 delta)^3 / (ux uy uz), with D the voxel diagonal and
+    // delta = D / (2 hist_width): each hat is 1-Lipschitz in bin units, and
+    // int min(1, 1 + delta - |t|) dt = 1 + 2 delta.  So a bin stays below
+    // gmax * 2^S * 1.003 * NW + (half a unit of rounding for each of at most NS voxels in its
+    // support) < 0xE0000000; a bin that reads back >= 0xF0000000 holds a (tiny) NEGATIVE sum
+    // of contributions with barycentric weights in [-bary_eps, 0).  A single contribution
+    // stays below 2^22 (the magic-number rounding below).
+    float fx_scale = 1.0f;
+    {
+        const float gmax = sqrtf(m2) * 1.001f;
+        const float D = sqrtf(uxf * uxf + uyf * uyf + uzf * uzf);
+        const float side = 2.0f * K.hw + D;
+        const float NS = side * side * side * iux * iuy * iuz * 1.01f + 64.0f;
+        const float wside = K.hw + D;  // hist_width * (1 + 2 delta)
+        const float NW = wside * wside * wside * iux * iuy * iuz * 1.01f + 1.0f;
+        const float lim = fminf((3.7e9f - 0.5f * NS) / (NW * 1.003f), 4.0e6f);
+        if (gmax > 0.0f && lim > 0.0f) {
+            int ex;
+            frexpf(lim / gmax, &ex);  // lim / gmax = m * 2^ex, m in [0.5, 1)
+            ex = min(max(ex - 1, -100), 100);
+            fx_scale = ldexpf(1.0f, ex);
+        }
+    }
+    __syncthreads();
+
+    float ibf[3] = {(float)ib0, (float)ib1, (float)ib2};
+    asm volatile("" : "+f"(ibf[0]), "+f"(ibf[1]), "+f"(ibf[2]));  // keep, do not re-derive from tid
+    const unsigned cell_addr = h_addr + 4u * (unsigned)(ib0 + 8 * ib1 + 68 * ib2);
+    unsigned ring_addr = sb + (unsigned)offsetof(D3Smem, ring) + 8u * (unsigned)(warp * D3_RING * 32 + lane);
+    asm volatile("" : "+r"(ring_addr));
+    int wr = 0, nq = 0;   // ring write slot, queued rows
+    int rem = 0;          // voxels left in the current row
+    float xf = 0.0f;
+    unsigned yz = 0;      // y | z << 16 of the current row
+    unsigned vidx = 0;    // voxel index of the current voxel in the level
+    const float mag_scale = fx_scale;
+
+    for (;;) {
+        const bool starving = rem == 0 && nq == 0 && !scan_done;
+        if (__any_sync(0xffffffffu, starving)) {
+            // a round of four rows for every lane that has room in its queue
+            int4 cur = S.cur[tid];
+            const float inv_by = __frcp_rn((float)cur.z);
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                if (nq < D3_RING && cur.x < cur.y) {
+                    const int dz = (int)(((float)cur.x + 0.5f) * inv_by);
+                    const int y = (cur.w & 0xffff) + (cur.x - dz * cur.z), z = (cur.w >> 16) + dz;
+                    int xa, cnt;
+                    d3_scan_row(S.scan, ibf, y, z, xa, cnt);
+                    if (cnt > 0) {
+                        sts_u2(ring_addr + 256u * (unsigned)wr, (unsigned)xa | ((unsigned)cnt << 16),
+                               (unsigned)y | ((unsigned)z << 16));
+                        wr = (wr + 1) & (D3_RING - 1);
+                        nq++;
+                    }
+                    cur.x += 4;
+                }
+            }
+            S.cur[tid].x = cur.x;
+            scan_done = cur.x >= cur.y;
+            continue;
+        }
+        const bool active = rem > 0 || nq > 0;
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (!active) continue;
+        if (rem == 0) {  // next queued row
+            const uint2 rec = lds_u2(ring_addr + 256u * (unsigned)((wr - nq) & (D3_RING - 1)));
+            nq--;
+            const unsigned xa = rec.x & 0xffffu;
+            rem = (int)(rec.x >> 16);
+            yz = rec.y;
+            xf = (float)xa;
+            vidx = xa + (unsigned)nx * ((yz & 0xffffu) + (unsigned)ny * (yz >> 16));
+        }
+        // ---- one voxel (sift.c:1866-1905) --------------------------------------------------
+        float sq, dv[3];
+        const bool member = d3_member(K, ibf, ld_shared_f32(kc_addr), xf, (float)(yz & 0xffffu),
+                                      (float)(yz >> 16), sq, dv);
+        const unsigned vi = vidx;
+        xf = fa(xf, 1.0f);
+        vidx++;
+        rem--;
+        if (!member) continue;
+        const float4 g4 = __ldg(gim + vi);
+        float g[3] = {g4.x, g4.y, g4.z};
+        // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument, glibc's expf
+        const float wgt_win = expf_glibc_t(__fdiv_rn(fm(-0.5f, sq), ld_shared_f32(kc_addr + 4u)), etab);
+        g[0] = fm(g[0], wgt_win);
+        g[1] = fm(g[1], wgt_win);
+        g[2] = fm(g[2], wgt_win);
+        float gr[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            gr[a] = dot3(K.Rt[3 * a], g[0], K.Rt[3 * a + 1], g[1], K.Rt[3 * a + 2], g[2]);
+        float bary[3];
+        const int bin = icos_bin_t(faces, gr, bary, FAST);
+        if (bin < 0) continue;
+        const float mag = __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
+        // mag * 2^S: scaling by a power of two commutes with every rounding below (sift.c:1763-1765)
+        const float mag_s = fm(mag, mag_scale);
+        const unsigned va0 = cell_addr + (unsigned)faces.idx<0>(bin);
+        const unsigned va1 = cell_addr + (unsigned)faces.idx<1>(bin);
+        const unsigned va2 = cell_addr + (unsigned)faces.idx<2>(bin);
+        // trilinear weights (1-dx | dx)(1-dy | dy)(1-dz | dz), products associated as in the
+        // reference: (x * y) * z
+        const float wx0 = fs(1.0f, dv[0]), wy0 = fs(1.0f, dv[1]), wz0 = fs(1.0f, dv[2]);
+        const float wxy[4] = {fm(wx0, wy0), fm(wx0, dv[1]), fm(dv[0], wy0), fm(dv[0], dv[1])};
+        // contribution (mag * w) * bary (sift.c:1763-1765) rounded to an integer: one FMA with
+        // the magic constant rounds the exact product once, on the FMA pipe (a float-to-int
+        // conversion is a quarter-rate instruction, and there are 24 per voxel)
+#define S3D_CORNER3(DX, DY, DZ)                                                                    \
+    {                                                                                              \
+        constexpr int COFF = 4 * ((DX) + 8 * (DY) + 68 * (DZ));                                    \
+        const float mw = fm(mag_s, fm(wxy[2 * (DX) + (DY)], (DZ) ? dv[2] : wz0));                  \
+        red_add_off<COFF>(va0, __float_as_uint(__fmaf_rn(mw, bary[0], D3_MAGIC)) - D3_MAGIC_BITS); \
+        red_add_off<COFF>(va1, __float_as_uint(__fmaf_rn(mw, bary[1], D3_MAGIC)) - D3_MAGIC_BITS); \
+        red_add_off<COFF>(va2, __float_as_uint(__fmaf_rn(mw, bary[2], D3_MAGIC)) - D3_MAGIC_BITS); \
+    }
+        S3D_CORNER3(0, 0, 0)
+        S3D_CORNER3(0, 0, 1)
+        S3D_CORNER3(0, 1, 0)
+        S3D_CORNER3(0, 1, 1)
+        S3D_CORNER3(1, 0, 0)
+        S3D_CORNER3(1, 0, 1)
+        S3D_CORNER3(1, 1, 0)
+        S3D_CORNER3(1, 1, 1)
+#undef S3D_CORNER3
+    }
+    __syncthreads();
+
+    // fixed point -> f32 (interior cells of the padded layout)
+    {
+        const double inv = 1.0 / (double)fx_scale;
+        for (int i = tid; i < S3D_DESC_NUMEL; i += D3_THREADS) {
+            const int cellv = i / 12, v12 = i - 12 * cellv;
+            const unsigned u = S.h[v12 * D3_VSTRIDE + (cellv & 3) + 8 * ((cellv >> 2) & 3) + 68 * (cellv >> 4)];
+            const long long v = u >= 0xF0000000u ? (long long)u - 4294967296ll : (long long)u;
+            hist[i] = (float)((double)v * inv);
+        }
+    }
+    __syncthreads();
+
+    // normalize_desc (sift.c:1794-1821), truncate (sift.c:1909-1915), normalize again
+    const float trunc = (float)((double)(0.2f * 128.0f / S3D_DESC_NUMEL));
+    for (int pass = 0; pass < 2; pass++) {
+        double acc = 0.0;
+        for (int i = tid; i < S3D_DESC_NUMEL; i += D3_THREADS) {
+            const double v = (double)hist[i];
+            acc = __dadd_rn(acc, __dmul_rn(v, v));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < D3_THREADS / 32; i++) tot += s_red[i];
+            s_norm_inv = (float)(1.0 / (sqrt(tot) + DBL_EPSILON));
+        }
+        __syncthreads();
+        const float ninv = s_norm_inv;
+        for (int i = tid; i < S3D_DESC_NUMEL; i += D3_THREADS) {
+            float v = fm(hist[i], ninv);
+            if (pass == 0) v = fminf(v, trunc);
+            hist[i] = v;
+        }
+        __syncthreads();
+    }
+    float *o32 = reinterpret_cast<float *>(out + (size_t)ki * S3D_DESC_STRIDE);
+    for (int i = tid; i < S3D_DESC_NUMEL; i += D3_THREADS) o32[i] = hist[i];
+    if (tid == 0) {
+        double *o64 = reinterpret_cast<double *>(out + (size_t)ki * S3D_DESC_STRIDE +
+                                                 S3D_DESC_NUMEL * sizeof(float));
+        const double f = ldexp(1.0, kp.o);  // sift.c:1851, 1922-1925
+        o64[0] = (double)kp.x * f;
+        o64[1] = (double)kp.y * f;
+        o64[2] = (double)z_global * f;
+        o64[3] = kp.sd;
+    }
+}
+
 // ---------------------------------------------------------------- dense descriptors
 // extract_dense_descriptors_no_rotate (sift.c:2462-2480): barycentric weights of
 // the gradient direction, written to three of the twelve channels.
@@ -1656,20 +1998,38 @@ __global__ void __launch_bounds__(256)
 // both assign_eig_ori (sift.c:1385) and extract_descrip (sift.c:1882) evaluate per visit.
 __global__ void __launch_bounds__(256)
     k_gradient(const float *__restrict__ im, int nx, int ny, int nz, float iux, float iuy,
-               float iuz, float4 *__restrict__ out)
-{   // grid: (ceil(nx / 256), ny, nz) -- one voxel per thread, no index division
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
-    if (x >= nx) return;
-    const size_t ys = nx, zs = (size_t)nx * ny;
-    const size_t idx = x + y * ys + z * zs;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
-        const float *p = im + idx;
-        g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
-        g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
-        g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+               float iuz, float4 *__restrict__ out, float *__restrict__ bmax, int nbx, int nby)
+{   // grid: (ceil(nx / 32), ceil(ny / 8), nz), block (32, 8): one voxel per thread, no index
+    // division.  Also leaves max |g|^2 over every 8 x 8 x 1 block of voxels in bmax[z][y/8][x/8]
+    // (k_descriptor3 bounds the gradient magnitude inside a window with it).
+    __shared__ float s_m[8][4];
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, z = blockIdx.z;
+    float m2 = 0.0f;
+    if (x < nx && y < ny) {
+        const size_t ys = nx, zs = (size_t)nx * ny;
+        const size_t idx = x + y * ys + z * zs;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
+            const float *p = im + idx;
+            g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+            g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+            g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+        }
+        out[idx] = g;
+        m2 = g.x * g.x + g.y * g.y + g.z * g.z;
     }
-    out[idx] = g;
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 4));
+    if ((threadIdx.x & 7) == 0) s_m[threadIdx.y][threadIdx.x >> 3] = m2;
+    __syncthreads();
+    if (threadIdx.y == 0 && threadIdx.x < 4) {
+        float m = s_m[0][threadIdx.x];
+#pragma unroll
+        for (int r = 1; r < 8; r++) m = fmaxf(m, s_m[r][threadIdx.x]);
+        const int bxi = blockIdx.x * 4 + threadIdx.x;
+        if (bxi < nbx) bmax[((size_t)z * nby + blockIdx.y) * nbx + bxi] = m;
+    }
 }
 
 PyrTable make_table(const s3d_engine *e)
@@ -1721,7 +2081,9 @@ int s3d_gradients_prepare(s3d_engine *e)
             if (e->grad[lv]) cudaFree(e->grad[lv]);
             e->grad[lv] = nullptr;
             e->grad_cap[lv] = 0;
-            if (cudaMalloc(&e->grad[lv], l.n() * sizeof(float4)) != cudaSuccess) {
+            // the gradient volume, then the per-plane 8x8 block maxima of |g|^2 (k_gradient)
+            const size_t nbm = (size_t)((l.g.nx + 7) / 8) * ((l.g.ny + 7) / 8) * l.g.nz;
+            if (cudaMalloc(&e->grad[lv], l.n() * sizeof(float4) + nbm * sizeof(float)) != cudaSuccess) {
                 cudaGetLastError();  // out of memory: this level stays on the scalar path
                 e->grad[lv] = nullptr;
                 continue;
@@ -1729,16 +2091,16 @@ int s3d_gradients_prepare(s3d_engine *e)
             e->grad_cap[lv] = l.n();
         }
         const float ux = (float)l.g.ux, uy = (float)l.g.uy, uz = (float)l.g.uz;
-        if (l.g.ny > 65535 || l.g.nz > 65535) {  // grid.y / grid.z limits: scalar path
+        if (l.g.ny > 65535 || l.g.nz > 65535 || l.n() >= ((size_t)1 << 32)) {  // grid limits, 32-bit voxel index: scalar path
             cudaFree(e->grad[lv]);
             e->grad[lv] = nullptr;
             e->grad_cap[lv] = 0;
             continue;
         }
-        const int bdx = l.g.nx >= 256 ? 256 : ((l.g.nx + 31) / 32) * 32;
-        k_gradient<<<dim3((l.g.nx + bdx - 1) / bdx, l.g.ny, l.g.nz), bdx, 0, e->stream>>>(
+        const int nbx = (l.g.nx + 7) / 8, nby = (l.g.ny + 7) / 8;
+        k_gradient<<<dim3((l.g.nx + 31) / 32, nby, l.g.nz), dim3(32, 8), 0, e->stream>>>(
             l.d, l.g.nx, l.g.ny, l.g.nz, __fdiv_rn_host(ux), __fdiv_rn_host(uy), __fdiv_rn_host(uz),
-            e->grad[lv]);
+            e->grad[lv], reinterpret_cast<float *>(e->grad[lv] + l.n()), nbx, nby);
         S3D_LAUNCH_CHECK(e);
     }
     S3D_CUDA(e, cudaMemcpyAsync(e->d_level_gptrs, e->grad.data(), L * sizeof(float4 *),
@@ -1933,12 +2295,31 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
     return 0;
 }
 
-int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out)
+int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned char *d_out,
+                      int kp_levels_only)
 {
     if (n <= 0) return 0;
     if (!e->have_mesh) return s3d_fail(e, "mesh not set", cudaSuccess, __FILE__, __LINE__);
     if (s3d_gradients_prepare(e)) return -1;
     const PyrTable T = make_table(e);
+    // k_descriptor3 needs the gradient volume (and its block maxima) of every level a keypoint
+    // can name: the caller vouches that all keypoints sit on keypoint levels s = 0..K-1, and all
+    // of those must have got their volume (s3d_gradients_prepare is best effort)
+    bool v3 = kp_levels_only && e->grad_valid && !e->opt_desc_v1 && !e->opt_desc_path && !e->opt_desc_v2;
+    for (int lv = 0; v3 && lv < (int)e->g.size(); lv++) {
+        const int sidx = lv % e->nlev_g + e->first_level;
+        if (sidx >= 0 && sidx < e->K && !e->grad[lv]) v3 = false;
+    }
+    if (v3) {
+        if (!(e->opt_icos_fast & 1))
+            k_descriptor3<4, false><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+        else if (e->opt_desc_occ == 3)
+            k_descriptor3<3, true><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+        else
+            k_descriptor3<4, true><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+        S3D_LAUNCH_CHECK(e);
+        return 0;
+    }
     // v2 packs window offsets in 10 bits per axis; a window wider than 1023 voxels (absurd
     // scales) takes the simple kernel
     if (e->opt_desc_v1)

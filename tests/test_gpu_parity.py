@@ -279,9 +279,39 @@ def test_full_size_properties(b200_lib):
     assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-3
 
 
+def test_descriptor_kernels_agree(b200_lib):
+    """k_descriptor3 (cell-owner lanes, the default) against k_descriptor2 (raster-order rows,
+    option `desc_v2`): both are exact integer accumulations of the same visited set at different
+    fixed-point scales, so they agree to the rounding of the contributions (<= 1e-5 relative L2),
+    and each is bit-reproducible from run to run."""
+    from sift3d_b200 import capi
+    from sift3d_b200.volumes import blob_volume
+    cu = C.CDLL(str(capi.CUDA_LIB))
+    cu.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    b200_lib.lib.sift3d_b200_engine.restype = C.c_void_p
+    b200_lib.lib.sift3d_b200_engine.argtypes = [C.POINTER(capi.SIFT3D)]
+    rng = np.random.default_rng(5)
+    cases = [(blob_volume((72, 80, 96), seed=31), (1.0, 1.0, 1.0)),
+             (blob_volume((48, 52, 60), seed=23), (1.0, 1.3, 0.8)),
+             (rng.random((40, 44, 48), dtype=np.float32), (1.0, 1.0, 1.0))]
+    for vol, units in cases:
+        with capi.Sift3D(b200_lib) as s:
+            kp = s.detect_keypoints(vol, units=units)
+            assert len(kp) > 10
+            eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+            d3 = s.extract_descriptors()["hists"].copy()
+            assert np.array_equal(s.extract_descriptors()["hists"], d3)
+            try:
+                assert cu.s3d_set_option(eng, b"desc_v2", 1) == 0
+                d2 = s.extract_descriptors()["hists"].copy()
+            finally:
+                cu.s3d_set_option(eng, b"desc_v2", 0)
+            assert rel_l2(d3, d2).max() <= 1e-5, rel_l2(d3, d2).max()
+
+
 def test_descriptor_fixed_point_paths_agree(b200_lib):
-    """The descriptor kernel's fallback accumulation paths (signed general, large-contribution,
-    legacy 2^-32 with 64-bit carry) are exact integer arithmetic like the default one: forced
+    """k_descriptor2's fallback accumulation paths (signed general, large-contribution,
+    legacy 2^-32 with 64-bit carry) are exact integer arithmetic like its default one: forced
     through the `desc_path` test hook they must reproduce its descriptors (bit for bit at the
     same scale; to f32 rounding for the 2^-32 variant)."""
     from sift3d_b200 import capi
@@ -295,6 +325,7 @@ def test_descriptor_fixed_point_paths_agree(b200_lib):
         kp = s.detect_keypoints(vol)
         assert len(kp) > 20
         eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+        cu.s3d_set_option(eng, b"desc_v2", 1)
         base = s.extract_descriptors()["hists"].copy()
         try:
             # 4 = untrimmed row intervals (phase B rejects the extra voxels itself), 5 = both:
@@ -318,6 +349,7 @@ def test_descriptor_fixed_point_paths_agree(b200_lib):
             if len(kp) == 0:
                 continue
             eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+            cu.s3d_set_option(eng, b"desc_v2", 1)
             base = s.extract_descriptors()["hists"].copy()
             try:
                 assert cu.s3d_set_option(eng, b"desc_path", 4) == 0
@@ -326,8 +358,6 @@ def test_descriptor_fixed_point_paths_agree(b200_lib):
                 cu.s3d_set_option(eng, b"desc_path", 0)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("S3D_EXPERIMENTAL") != "1",
-                    reason="experimental kernels are validated on request (S3D_EXPERIMENTAL=1)")
 def test_experimental_orient_stage_matches_default(b200_lib):
     """`orient_stage` (the warp-cooperative orientation kernel, default off, written without
     GPU time to measure it) must reproduce the default kernel's keypoints bit for bit -- same

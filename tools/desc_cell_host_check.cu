@@ -74,6 +74,8 @@ int main(int argc, char **argv)
         sphere_bounds(K.ky, win_radius, K.uy, ny, K.y0, K.y1);
         sphere_bounds(K.kz, win_radius, K.uz, nz, K.z0, K.z1);
         d3_key_finish(K);
+        D3Scan Q;
+        d3_scan_setup(K, Q);
 
         std::vector<unsigned char> ref((size_t)nx * ny * nz, 0), got((size_t)nx * ny * nz, 0);
         // the reference's visit set (any cell)
@@ -101,13 +103,13 @@ int main(int argc, char **argv)
             for (int z = C.zlo; z <= C.zhi; z++)
                 for (int y = C.ylo; y <= C.yhi; y++) {
                     int xa, cnt;
-                    d3_scan_row(K, C, y, z, xa, cnt);
+                    d3_scan_row(Q, C.ibf, y, z, xa, cnt);
                     tot_rows++;
                     bool hit = false;
                     for (int x = xa; x < xa + cnt; x++) {
                         float sq, dv[3];
                         nscan++;
-                        if (!d3_member(K, C, (float)x, (float)y, (float)z, sq, dv)) continue;
+                        if (!d3_member(K, C.ibf, K.r2, (float)x, (float)y, (float)z, sq, dv)) continue;
                         unsigned char &gg = got[x + (size_t)nx * (y + (size_t)ny * z)];
                         if (gg) dup++;
                         gg = 1;
@@ -127,7 +129,6 @@ int main(int argc, char **argv)
         }
         tot_ref += nref;
         tot_scan += nscan;
-        if (c < 16) printf("case %d mode %d aniso %d: ref %lld scanned x%.3f\n", c, mode, (int)aniso, nref, (double)nscan / (double)nref);
     }
     printf("%d cases, %lld voxels visited by the reference, %lld scanned (x%.4f), rows scanned %lld hit %lld (%.1f%%)\n",
            ncase, tot_ref, tot_scan, (double)tot_scan / (double)tot_ref, tot_rows, tot_rows_hit,
