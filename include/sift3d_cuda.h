@@ -129,6 +129,11 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
                           const double desc_units[3], const s3d_filter *smooth,
                           const s3d_filter *window, float *host_out);
 
+/* CUDA-event times of the last s3d_dense_descriptors call on the engine's stream:
+ * ms[0] upload, ms[1] kernels (smoothing, channel image, 12-channel blur, post-processing),
+ * ms[2] download.  -1 when no call has completed. */
+int s3d_dense_last_timing(const s3d_engine *e, double ms[3]);
+
 /* SIFT3D_extract_dense_descriptors, dense_rotate = 1 (sift.c:2521-2588, :2295-2343):
  * per voxel, assign_orientation_thresh with sigma = ori_sigma (identity when rejected),
  * then one 12-bin histogram over a sphere of radius 2 * desc_sigma, gradients rotated by
@@ -182,6 +187,11 @@ int s3d_slab_image_upload(s3d_engine *e, const float *host, size_t xs, size_t ys
 int s3d_slab_image_from_device(s3d_engine *e, const float *dev);
 /* info = {own0, own1, lo, hi, NZ, halo} of octave o: owned planes, planes held, global count. */
 int s3d_slab_info(const s3d_engine *e, int o, int info[6]);
+/* Communication of the last s3d_build_pyramid on a slab engine: out = {halo bytes sent, halo
+ * bytes received, exchanges, ms in halo exchanges, ms in all-reduces}; the two times are CUDA-event
+ * intervals on the engine's stream (they include waiting for the slower neighbour) and need
+ * s3d_set_option(e, "slab_timing", 1), else -1. */
+int s3d_slab_stats(s3d_engine *e, double out[5]);
 
 /* ---- descriptor matching -------------------------------------------
  * SIFT3D_nn_match / match_desc (sift.c:2840-2969): nearest + second-nearest by f64 SSD over

@@ -136,6 +136,8 @@ struct s3d_engine {
     size_t dense_cap[4] = {0, 0, 0, 0};
     void *stage[2] = {nullptr, nullptr};
     size_t stage_cap = 0;
+    cudaEvent_t dense_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double dense_ms[3] = {-1.0, -1.0, -1.0};  // upload, kernels, download of the last dense call
     int opt_dense_copy = 1;  // 1 = staged parallel download, 0 = plain cudaMemcpy into pageable memory
 
     // descriptor scratch
@@ -153,6 +155,13 @@ struct s3d_engine {
     std::vector<s3d_geom> slab_g;    // global geometry of the Gaussian levels
     int slab_halo = 0;               // halo planes kept around the owned range of every level
     int *d_level_zoff = nullptr;     // per gpyr level: global z of local plane 0 (0 when not tiled)
+    // statistics of the last s3d_slab_build_pyramid (s3d_slab_stats): halo bytes sent / received,
+    // number of exchanges, and -- with option "slab_timing" -- CUDA-event time spent in them
+    double slab_sent = 0, slab_recv = 0, slab_xchg_ms = 0, slab_allreduce_ms = 0;
+    int slab_nxchg = 0;
+    int opt_slab_timing = 0;
+    std::vector<cudaEvent_t> slab_ev;  // event pool of the timed exchanges
+    std::vector<int> slab_ev_kind;     // per event pair: 0 halo exchange, 1 all-reduce
 
     std::vector<SegTab> segtabs;
     long long *d_blur_dbg = nullptr;  // debug: per-CTA clocks of the last fused blur

@@ -145,7 +145,9 @@ __host__ __device__ __forceinline__ void d3_scan_row(const D3Scan &Q, const floa
     const float rem = Q.r2w - fmaf(vy, vy, vz * vz);
     if (rem < 0.0f) return;
 #ifdef __CUDA_ARCH__
-    const float hx = rem * rsqrtf(fmaxf(rem, 1e-30f)) * Q.iux;  // 2 ulp: far inside the widening
+    float rs;  // MUFU.RSQ, 2 ulp: far inside the widening (rem = 0 gives inf * 0: guarded)
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(rem, 1e-12f)));
+    const float hx = rem * rs * Q.iux;
 #else
     const float hx = sqrtf(rem) * Q.iux;
 #endif

@@ -197,6 +197,9 @@ void s3d_engine_destroy(s3d_engine *e)
         if (p) cudaFree(p);
     for (void *p : e->stage)
         if (p) cudaFreeHost(p);
+    for (cudaEvent_t ev : e->dense_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->slab_ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -234,6 +237,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "blur_mode")) e->blur_mode = value;
     else if (!strcmp(name, "desc_v1")) e->opt_desc_v1 = value;
     else if (!strcmp(name, "desc_v2")) e->opt_desc_v2 = value;
+    else if (!strcmp(name, "slab_timing")) e->opt_slab_timing = value;
     else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 7;
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
     else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
@@ -845,8 +849,14 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
         return -1;
     float *raw = e->dense_buf[0], *sm = e->dense_buf[1], *t12 = e->dense_buf[2], *d12 = e->dense_buf[3];
     int rc = -1;
+    for (int i = 0; i < 4; i++)  // device-side stage times of the call (s3d_dense_last_timing)
+        if (!e->dense_ev[i] && cudaEventCreate(&e->dense_ev[i]) != cudaSuccess) e->dense_ev[i] = nullptr;
+    const bool have_ev = e->dense_ev[0] && e->dense_ev[1] && e->dense_ev[2] && e->dense_ev[3];
+    e->dense_ms[0] = e->dense_ms[1] = e->dense_ms[2] = -1.0;
     do {
+        if (have_ev) cudaEventRecord(e->dense_ev[0], e->stream);
         if (upload_strided(e, raw, host_in, nx, ny, nz, xs, ys, zs)) break;
+        if (have_ev) cudaEventRecord(e->dense_ev[1], e->stream);
         if (trace) cudaStreamSynchronize(e->stream);
         t[1] = now_ms();
         // smooth_scale_raw_input (sift.c:1978-2006)
@@ -868,18 +878,31 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
         if (trace) cudaStreamSynchronize(e->stream);
         t[3] = now_ms();
         if (s3d_k_dense_post(e, d12, raw, n)) break;
+        if (have_ev) cudaEventRecord(e->dense_ev[2], e->stream);
         if (trace) cudaStreamSynchronize(e->stream);
         t[4] = now_ms();
         if (d2h_pageable(e, host_out, d12, n * 48)) break;
+        if (have_ev) cudaEventRecord(e->dense_ev[3], e->stream);
         t[5] = now_ms();
         rc = 0;
     } while (0);
     cudaStreamSynchronize(e->stream);
+    if (rc == 0 && have_ev)
+        for (int i = 0; i < 3; i++) {
+            float ms = -1.0f;
+            if (cudaEventElapsedTime(&ms, e->dense_ev[i], e->dense_ev[i + 1]) == cudaSuccess) e->dense_ms[i] = ms;
+        }
     if (trace && rc == 0)
         fprintf(stderr, "[s3d dense %dx%dx%d] alloc %.2f upload %.2f smooth+bary %.2f blur12 %.2f post %.2f "
                         "download %.2f ms\n", nx, ny, nz, 0.0, t[1] - t[0], t[2] - t[1], t[3] - t[2],
                 t[4] - t[3], t[5] - t[4]);
     return rc;
+}
+
+int s3d_dense_last_timing(const s3d_engine *e, double ms[3])
+{
+    for (int i = 0; i < 3; i++) ms[i] = e->dense_ms[i];
+    return e->dense_ms[1] >= 0.0 ? 0 : -1;
 }
 
 int s3d_dense_descriptors_rotate(s3d_engine *e, const float *host_in, int nx, int ny, int nz,

@@ -299,6 +299,18 @@ static void halo_plan(int nranks, int noct, const int *own, int o, int NZ, int h
     }
 }
 
+// CUDA events around a communication step (option "slab_timing"): pairs are summed after the
+// pyramid is built.  The interval also contains the wait for the slower neighbour.
+static void slab_mark(s3d_engine *e, int kind, bool begin)
+{
+    if (!e->opt_slab_timing) return;
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, e->stream);
+    e->slab_ev.push_back(ev);
+    if (begin) e->slab_ev_kind.push_back(kind);
+}
+
 static int slab_exchange(s3d_engine *e, float *base, int o, int h)
 {
     s3d_comm *c = e->comm;
@@ -312,10 +324,15 @@ static int slab_exchange(s3d_engine *e, float *base, int o, int h)
         (x.kind ? recvs : sends)
             .push_back({x.peer, base + (size_t)(x.z0 - S.lo) * plane,
                         (size_t)(x.z1 - x.z0) * plane * sizeof(float)});
+    for (const Xfer &x : sends) e->slab_sent += (double)x.bytes;
+    for (const Xfer &x : recvs) e->slab_recv += (double)x.bytes;
+    if (!sends.empty() || !recvs.empty()) e->slab_nxchg++;
+    slab_mark(e, 0, true);
     if (c->exchange(sends, recvs, e->stream, e->device)) {
         e->err = c->err;
         return -1;
     }
+    slab_mark(e, 0, false);
     return 0;
 }
 
@@ -327,15 +344,22 @@ int s3d_slab_build_pyramid(s3d_engine *e)
     const SlabOct &S0 = e->slab[0];
     const s3d_geom &G0 = e->slab_g[0];
     const size_t plane0 = (size_t)G0.nx * G0.ny;
+    e->slab_sent = e->slab_recv = e->slab_xchg_ms = e->slab_allreduce_ms = 0.0;
+    e->slab_nxchg = 0;
+    for (cudaEvent_t ev : e->slab_ev) cudaEventDestroy(ev);
+    e->slab_ev.clear();
+    e->slab_ev_kind.clear();
     S3D_CUDA(e, cudaMemsetAsync(e->d_scalars, 0, e->n_scalars * sizeof(unsigned), e->stream));
     // im_scale (imutil.c:1977-1991): max over the owned planes, then over the ranks
     float *own_im = e->im + (size_t)(S0.own0 - S0.lo) * plane0;
     const size_t n_own = (size_t)(S0.own1 - S0.own0) * plane0;
     if (n_own && s3d_k_max_abs(e, own_im, n_own, e->d_scalars)) return -1;
+    slab_mark(e, 1, true);
     if (c->allreduce_max_u32(e->d_scalars, 1, e->stream, e->device)) {
         e->err = c->err;
         return -1;
     }
+    slab_mark(e, 1, false);
     if (n_own && s3d_k_scale(e, own_im, own_im, n_own, e->d_scalars)) return -1;
     float uf[3];
     auto level_uf = [&](const s3d_geom &g) {
@@ -387,10 +411,36 @@ int s3d_slab_build_pyramid(s3d_engine *e)
                           e->dog[(size_t)o * nld + s].d + off, n, e->d_scalars + 1 + (size_t)o * nld + s))
                 return -1;
     }
+    slab_mark(e, 1, true);
     if (c->allreduce_max_u32(e->d_scalars, e->n_scalars, e->stream, e->device)) {
         e->err = c->err;
         return -1;
     }
+    slab_mark(e, 1, false);
+    return 0;
+}
+
+int s3d_slab_stats(s3d_engine *e, double out[5])
+{
+    if (e->slab.empty()) return -1;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(e->device);
+    if (!e->slab_ev.empty()) {  // timed run: sum the event pairs once
+        cudaStreamSynchronize(e->stream);
+        e->slab_xchg_ms = e->slab_allreduce_ms = 0.0;
+        for (size_t i = 0; 2 * i + 1 < e->slab_ev.size() && i < e->slab_ev_kind.size(); i++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, e->slab_ev[2 * i], e->slab_ev[2 * i + 1]) == cudaSuccess)
+                (e->slab_ev_kind[i] ? e->slab_allreduce_ms : e->slab_xchg_ms) += ms;
+        }
+    }
+    out[0] = e->slab_sent;
+    out[1] = e->slab_recv;
+    out[2] = (double)e->slab_nxchg;
+    out[3] = e->opt_slab_timing ? e->slab_xchg_ms : -1.0;
+    out[4] = e->opt_slab_timing ? e->slab_allreduce_ms : -1.0;
+    if (prev >= 0) cudaSetDevice(prev);
     return 0;
 }
 
