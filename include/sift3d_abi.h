@@ -230,6 +230,11 @@ int write_SIFT3D_Descriptor_store(const char *path, const SIFT3D_Descriptor_stor
 /* ---- B200 extensions (not in the reference) -------------------------------- */
 /* Materialise pyramid level (o,s) from HBM into host memory (which: 0 Gaussian, 1 DoG). */
 int sift3d_b200_fetch_level(const SIFT3D *sift3d, int which, int o, int s, float *dst);
+/* Host copies of every level in gpyr.levels[i].data / dog.levels[i].data (malloc memory owned by
+ * the SIFT3D object), for callers that read the pyramids as they would after the reference's
+ * detect (write_pyramid imutil.c:4093, copy_SIFT3D sift.c:650-651).  $SIFT3D_HOST_PYRAMID=1
+ * makes every SIFT3D_detect_keypoints end with it. */
+int sift3d_b200_materialize_pyramids(SIFT3D *sift3d);
 /* Opaque engine behind a SIFT3D object (s3d_engine*, include/sift3d_cuda.h), or NULL. */
 void *sift3d_b200_engine(const SIFT3D *sift3d);
 /* Number of candidates found by the last detect (before orientation rejection). */

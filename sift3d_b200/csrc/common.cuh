@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a tool is attached
 
 #include <cmath>
 #include <cstdint>
@@ -172,6 +173,13 @@ struct s3d_engine {
     int *d_level_dims = nullptr;     // nx,ny,nz per gpyr level
     float *d_level_units = nullptr;  // (float)ux,uy,uz per gpyr level
     double *d_level_scales = nullptr;  // Image.s per gpyr level
+};
+
+// NVTX range per pipeline stage (nsys / ncu --nvtx): "s3d:upload", "s3d:pyramid", "s3d:extrema",
+// "s3d:orientation", "s3d:descriptors", "s3d:dense", "s3d:halo_exchange"
+struct S3dRange {
+    explicit S3dRange(const char *name) { nvtxRangePushA(name); }
+    ~S3dRange() { nvtxRangePop(); }
 };
 
 int s3d_fail(s3d_engine *e, const char *what, cudaError_t ce, const char *file, int line);

@@ -287,21 +287,28 @@ int s3d_pyramid_resize(s3d_engine *e, int num_octaves, int num_kp_levels, const 
         e->first_level = -1;
         e->g.resize((size_t)num_octaves * nlev_g);
         e->dog.resize((size_t)num_octaves * nlev_d);
-        for (int i = 0; i < num_octaves * nlev_g; i++) {
+        // a failed allocation must not leave a half-built pyramid that the `same` fast path of
+        // the next call would accept: free everything (noct back to 0) before reporting
+        cudaError_t ce = cudaSuccess;
+        for (int i = 0; ce == cudaSuccess && i < num_octaves * nlev_g; i++) {
             e->g[i].g = gpyr[i];
-            S3D_CUDA(e, cudaMalloc(&e->g[i].d, e->g[i].n() * sizeof(float)));
+            ce = cudaMalloc(&e->g[i].d, e->g[i].n() * sizeof(float));
         }
-        for (int i = 0; i < num_octaves * nlev_d; i++) {
+        for (int i = 0; ce == cudaSuccess && i < num_octaves * nlev_d; i++) {
             e->dog[i].g = dog[i];
-            S3D_CUDA(e, cudaMalloc(&e->dog[i].d, e->dog[i].n() * sizeof(float)));
+            ce = cudaMalloc(&e->dog[i].d, e->dog[i].n() * sizeof(float));
         }
         const int L = num_octaves * nlev_g;
-        S3D_CUDA(e, cudaMalloc(&e->d_level_ptrs, L * sizeof(float *)));
-        S3D_CUDA(e, cudaMalloc(&e->d_level_dims, 3 * L * sizeof(int)));
-        S3D_CUDA(e, cudaMalloc(&e->d_level_units, 3 * L * sizeof(float)));
-        S3D_CUDA(e, cudaMalloc(&e->d_level_scales, L * sizeof(double)));
         e->n_scalars = 1 + num_octaves * nlev_d;
-        S3D_CUDA(e, cudaMalloc(&e->d_scalars, e->n_scalars * sizeof(unsigned)));
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_level_ptrs, L * sizeof(float *));
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_level_dims, 3 * L * sizeof(int));
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_level_units, 3 * L * sizeof(float));
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_level_scales, L * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc(&e->d_scalars, e->n_scalars * sizeof(unsigned));
+        if (ce != cudaSuccess) {
+            free_pyramid(e);
+            return s3d_fail(e, "s3d_pyramid_resize: cudaMalloc", ce, __FILE__, __LINE__);
+        }
     }
     if (num_octaves == 0) return 0;
     const int L = num_octaves * nlev_g;
@@ -394,6 +401,7 @@ static int upload_strided(s3d_engine *e, float *dev, const float *host, int nx, 
 int s3d_image_upload(s3d_engine *e, const float *host, int nx, int ny, int nz, size_t xs,
                      size_t ys, size_t zs)
 {
+    S3dRange nvtx_range("s3d:upload");
     DeviceGuard guard(e->device);
     if (ensure_im(e, nx, ny, nz)) return -1;
     return upload_strided(e, e->im, host, nx, ny, nz, xs, ys, zs);
@@ -410,6 +418,7 @@ int s3d_image_from_device(s3d_engine *e, const float *dev, int nx, int ny, int n
 
 int s3d_build_pyramid(s3d_engine *e)
 {
+    S3dRange nvtx_range("s3d:pyramid");
     DeviceGuard guard(e->device);
     if (e->noct < 1 || !e->im || (int)e->oct_taps.size() != e->nlev_g - 1)
         return s3d_fail(e, "s3d_build_pyramid: pyramid/filters/image not configured", cudaSuccess,
@@ -465,6 +474,7 @@ int s3d_build_pyramid(s3d_engine *e)
 
 int s3d_detect_extrema(s3d_engine *e, double peak_thresh, int *num_candidates)
 {
+    S3dRange nvtx_range("s3d:extrema");
     DeviceGuard guard(e->device);
     if (e->noct < 1)
         return s3d_fail(e, "s3d_detect_extrema: no pyramid", cudaSuccess, __FILE__, __LINE__);
@@ -494,6 +504,7 @@ int s3d_detect_extrema(s3d_engine *e, double peak_thresh, int *num_candidates)
 
 int s3d_assign_orientations(s3d_engine *e, double corner_thresh, int *num_keypoints)
 {
+    S3dRange nvtx_range("s3d:orientation");
     DeviceGuard guard(e->device);
     if (s3d_k_orientations(e, corner_thresh)) return -1;
     int nkp = 0;
@@ -535,6 +546,7 @@ int s3d_num_keypoints(const s3d_engine *e) { return e->nkp; }
 int s3d_extract_descriptors_device(s3d_engine *e, const s3d_keypoint *dev_kp, int n,
                                    void *dev_desc)
 {
+    S3dRange nvtx_range("s3d:descriptors");
     DeviceGuard guard(e->device);
     if (e->noct < 1)
         return s3d_fail(e, "s3d_extract_descriptors: no pyramid", cudaSuccess, __FILE__, __LINE__);
@@ -551,6 +563,7 @@ int s3d_extract_descriptors_device(s3d_engine *e, const s3d_keypoint *dev_kp, in
 
 int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *host_desc)
 {
+    S3dRange nvtx_range("s3d:descriptors");
     DeviceGuard guard(e->device);
     if (n < 1) return s3d_fail(e, "s3d_extract_descriptors: n < 1", cudaSuccess, __FILE__, __LINE__);
     if (e->noct < 1)
@@ -837,6 +850,7 @@ int s3d_dense_descriptors(s3d_engine *e, const float *host_in, int nx, int ny, i
                           const double desc_units[3], const s3d_filter *smooth,
                           const s3d_filter *window, float *host_out)
 {
+    S3dRange nvtx_range("s3d:dense");
     DeviceGuard guard(e->device);
     const size_t n = (size_t)nx * ny * nz;
     TapSet ts, tw;
@@ -910,6 +924,7 @@ int s3d_dense_descriptors_rotate(s3d_engine *e, const float *host_in, int nx, in
                                  const s3d_filter *smooth, double ori_sigma, double desc_sigma,
                                  double corner_thresh, float *host_out)
 {
+    S3dRange nvtx_range("s3d:dense_rotate");
     DeviceGuard guard(e->device);
     const size_t n = (size_t)nx * ny * nz;
     TapSet ts;

@@ -313,6 +313,7 @@ static void slab_mark(s3d_engine *e, int kind, bool begin)
 
 static int slab_exchange(s3d_engine *e, float *base, int o, int h)
 {
+    S3dRange nvtx_range("s3d:halo_exchange");
     s3d_comm *c = e->comm;
     const SlabOct &S = e->slab[o];
     const s3d_geom &g0 = e->slab_g[(size_t)o * e->nlev_g];
@@ -596,8 +597,25 @@ int s3d_slab_halo_plan(int nranks, int num_octaves, const int *own, int o, int N
     return (int)plan.size();
 }
 
+static int slab_pyramid_resize_impl(s3d_engine *e, s3d_comm *comm, int num_octaves, int num_kp_levels,
+                                    const s3d_geom *gpyr, const s3d_geom *dog, const int *zsplit);
+
 int s3d_slab_pyramid_resize(s3d_engine *e, s3d_comm *comm, int num_octaves, int num_kp_levels,
                             const s3d_geom *gpyr, const s3d_geom *dog, const int *zsplit)
+{
+    // a failure half way (cudaMalloc) must not leave geometry that the `same` fast path of the
+    // next call would accept with null level pointers: drop everything
+    const int rc = slab_pyramid_resize_impl(e, comm, num_octaves, num_kp_levels, gpyr, dog, zsplit);
+    if (rc) {
+        const std::string msg = e->err;
+        s3d_free_pyramid(e);
+        e->err = msg;
+    }
+    return rc;
+}
+
+static int slab_pyramid_resize_impl(s3d_engine *e, s3d_comm *comm, int num_octaves, int num_kp_levels,
+                                    const s3d_geom *gpyr, const s3d_geom *dog, const int *zsplit)
 {
     int prev = -1;
     cudaGetDevice(&prev);

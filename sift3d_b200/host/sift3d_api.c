@@ -41,6 +41,12 @@ const double ori_rad_fctr = 3.0;   /* sift.c:52 */
 const double desc_sig_fctr = 7.071067812;
 const double desc_rad_fctr = 2.0;  /* sift.c:54 */
 const double gr = 1.6180339887;
+/* internal parameters the reference also exports as data symbols (sift.c:48-55); the device
+ * kernels carry the same values (keypoint.cu) */
+const double max_eig_ratio = 0.90;
+const double ori_grad_thresh = 1E-10;
+const double bary_eps = FLT_EPSILON * 1E1;
+const double trunc_thresh = 0.2f * 128.0f / 768;
 
 #define ERR(...) fprintf(stderr, __VA_ARGS__)
 #define MAXV(a, b) ((a) > (b) ? (a) : (b))
@@ -284,12 +290,26 @@ static int pyr_set_scales(double sigma0, double sigma_n, Pyramid *pyr)
     return SIFT3D_SUCCESS;
 }
 
-/* resize_Pyramid, imutil.c:3858-3947 -- metadata only: the voxel data of every
- * level lives in HBM (Image.data stays NULL; see sift3d_b200_fetch_level). */
+/* host copies of level data exist only after sift3d_b200_materialize_pyramids */
+static void pyr_free_host_data(Pyramid *pyr, int total)
+{
+    int i;
+    if (!pyr->levels) return;
+    for (i = 0; i < total; i++) {
+        free(pyr->levels[i].data);
+        pyr->levels[i].data = NULL;
+        pyr->levels[i].size = 0;
+    }
+}
+
+/* resize_Pyramid, imutil.c:3858-3947 -- metadata only: the voxel data of every level lives
+ * in HBM.  Image.data stays NULL until the caller asks for host copies
+ * (sift3d_b200_materialize_pyramids, or $SIFT3D_HOST_PYRAMID=1; see sift3d_b200_fetch_level). */
 static int pyr_resize(const Image *im, int have_image, int first_level, unsigned num_kp_levels,
                       unsigned num_levels, int first_octave, unsigned num_octaves, Pyramid *pyr)
 {
     const int total = (int)(num_levels * num_octaves);
+    const int pyr_old_total = pyr->levels ? pyr->num_levels * pyr->num_octaves : 0;
     double units[3];
     int dims[3], i, o, s;
     if (num_levels < num_kp_levels) {
@@ -301,6 +321,7 @@ static int pyr_resize(const Image *im, int have_image, int first_level, unsigned
     pyr->first_octave = first_octave;
     pyr->num_octaves = (int)num_octaves;
     pyr->num_levels = (int)num_levels;
+    pyr_free_host_data(pyr, pyr_old_total);
     if (total == 0) {
         free(pyr->levels);
         pyr->levels = NULL;
@@ -649,6 +670,8 @@ void cleanup_SIFT3D(SIFT3D *const sift3d)
     sift3d->kernels.downsample_2 = 0;
     free(sift3d->im.data);
     sift3d->im.data = NULL;
+    pyr_free_host_data(&sift3d->gpyr, sift3d->gpyr.num_levels * sift3d->gpyr.num_octaves);
+    pyr_free_host_data(&sift3d->dog, sift3d->dog.num_levels * sift3d->dog.num_octaves);
     free(sift3d->gpyr.levels);
     free(sift3d->dog.levels);
     sift3d->gpyr.levels = sift3d->dog.levels = NULL;
@@ -680,6 +703,11 @@ int copy_SIFT3D(const SIFT3D *const src, SIFT3D *const dst)
         if (resize_all(dst, src->gpyr.num_kp_levels)) return SIFT3D_FAILURE;
         memcpy(ds->resize_units, ss->resize_units, sizeof(ds->resize_units));
         if (push_geometry(dst, ds) || s3d_pyramid_copy(de, ss->eng)) return SIFT3D_FAILURE;
+        /* the reference copies the levels' host data too (sift.c:650-651): do so when the
+         * source has host copies */
+        if (src->gpyr.levels && src->gpyr.num_levels * src->gpyr.num_octaves > 0 &&
+            src->gpyr.levels[0].data && sift3d_b200_materialize_pyramids(dst))
+            return SIFT3D_FAILURE;
     }
     return SIFT3D_SUCCESS;
 }
@@ -752,9 +780,10 @@ int parse_args_SIFT3D(SIFT3D *const sift3d, const int argc, char **argv, const i
         case O_SIGMA0:
             set_sigma0_SIFT3D(sift3d, dval);
             break;
-        default:
+        default: /* '?' and, because optstring is "-", every non-option argument (c == 1):
+                  * the reference flags both when check_err is set (sift.c:844-848) */
             mine = 0;
-            if (check_err && c == '?') err = 1;
+            if (check_err) err = 1;
         }
         if (rc) {
             free(used);
@@ -860,6 +889,9 @@ static int detect_common(SIFT3D *const sift3d, const Image *const im, Keypoint_s
             "single-channel images are supported \n", im->nc);
         return SIFT3D_FAILURE;
     }
+    /* host copies of the previous pyramid (sift3d_b200_materialize_pyramids) are stale now */
+    pyr_free_host_data(&sift3d->gpyr, sift3d->gpyr.levels ? sift3d->gpyr.num_levels * sift3d->gpyr.num_octaves : 0);
+    pyr_free_host_data(&sift3d->dog, sift3d->dog.levels ? sift3d->dog.num_levels * sift3d->dog.num_octaves : 0);
     if (comm ? set_image_slab(sift3d, im, zsplit, comm) : set_image(sift3d, im))
         return SIFT3D_FAILURE;
     sl = slot_get(sift3d);
@@ -877,6 +909,9 @@ static int detect_common(SIFT3D *const sift3d, const Image *const im, Keypoint_s
         const Image *l = PYR_LEVEL(&sift3d->dog, 0, 0);
         kp->nx = l->nx, kp->ny = l->ny, kp->nz = l->nz;
     }
+    if (!comm && getenv("SIFT3D_HOST_PYRAMID") && atoi(getenv("SIFT3D_HOST_PYRAMID")) &&
+        sift3d_b200_materialize_pyramids(sift3d))
+        return SIFT3D_FAILURE;
     if (resize_Keypoint_store(kp, (size_t)nkp)) return SIFT3D_FAILURE;
     if (nkp == 0) return SIFT3D_SUCCESS;
     if ((tmp = (s3d_keypoint *)malloc((size_t)nkp * sizeof(s3d_keypoint))) == NULL)
@@ -1124,6 +1159,37 @@ int sift3d_b200_fetch_level(const SIFT3D *sift3d, int which, int o, int s, float
 {
     s3d_engine *e = engine_of(sift3d);
     return (!e || s3d_level_download(e, which, o, s, dst)) ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
+}
+
+/* Extension: host copies of every Gaussian and DoG level, so that code which reads
+ * sift3d->gpyr.levels[i].data / sift3d->dog.levels[i].data as it would after the reference's
+ * SIFT3D_detect_keypoints (write_pyramid, imutil.c:4093; copy_SIFT3D's deep copy,
+ * sift.c:650-651) finds the same bits there.  The data is malloc memory owned by the SIFT3D
+ * object (freed by cleanup_SIFT3D or the next resize) and is valid until the next detect
+ * call.  With $SIFT3D_HOST_PYRAMID=1 every SIFT3D_detect_keypoints ends with this call
+ * (6.3 GB of D2H for a 512^3 volume: opt-in). */
+int sift3d_b200_materialize_pyramids(SIFT3D *sift3d)
+{
+    s3d_engine *e = engine_of(sift3d);
+    int which, o, s;
+    if (!e || !SIFT3D_have_gpyr(sift3d)) return SIFT3D_FAILURE;
+    for (which = 0; which < 2; which++) {
+        Pyramid *pyr = which ? &sift3d->dog : &sift3d->gpyr;
+        for (o = pyr->first_octave; o < pyr->first_octave + pyr->num_octaves; o++)
+            for (s = pyr->first_level; s < pyr->first_level + pyr->num_levels; s++) {
+                Image *l = PYR_LEVEL(pyr, o, s);
+                const size_t n = (size_t)l->nx * l->ny * l->nz;
+                if (n == 0) continue;
+                if (l->size < n) {
+                    float *d = (float *)safe_realloc(l->data, n * sizeof(float));
+                    if (!d) return SIFT3D_FAILURE;
+                    l->data = d;
+                    l->size = n;
+                }
+                if (s3d_level_download(e, which, o, s, l->data)) return SIFT3D_FAILURE;
+            }
+    }
+    return SIFT3D_SUCCESS;
 }
 
 /* ============================================================ converters (host) */

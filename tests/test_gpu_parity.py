@@ -253,6 +253,44 @@ def test_copy_sift3d_keeps_pyramid(b200_lib):
         assert rc == 0 and rel_l2(b.descriptors()["hists"], da["hists"]).max() <= 1e-6
 
 
+def test_host_pyramid_materialisation(b200_lib, ref_lib):
+    """Callers that read sift3d->gpyr.levels[i].data after detect (write_pyramid,
+    imutil.c:4093) or after copy_SIFT3D (deep copy, sift.c:650-651): the extension
+    sift3d_b200_materialize_pyramids fills the host Images with the same bits the reference
+    leaves there, and copy_SIFT3D carries them over."""
+    from sift3d_b200 import capi
+    from sift3d_b200.volumes import blob_volume
+    vol = blob_volume((40, 44, 48), seed=12)
+    f = b200_lib.lib.sift3d_b200_materialize_pyramids
+    f.argtypes = [C.POINTER(capi.SIFT3D)]
+    f.restype = C.c_int
+
+    def host_levels(s):
+        out = []
+        for pyr in (s.s.gpyr, s.s.dog):
+            for i in range(pyr.num_levels * pyr.num_octaves):
+                im = pyr.levels[i]
+                assert bool(im.data), i
+                out.append(np.ctypeslib.as_array(im.data, shape=(im.nz, im.ny, im.nx)).copy())
+        return out
+
+    with capi.Sift3D(ref_lib) as r, capi.Sift3D(b200_lib) as g, capi.Sift3D(b200_lib) as c:
+        r.detect_keypoints(vol)
+        g.detect_keypoints(vol)
+        assert not bool(g.s.gpyr.levels[0].data)      # HBM only until asked
+        assert f(C.byref(g.s)) == 0
+        want, got = host_levels(r), host_levels(g)
+        assert len(want) == len(got)
+        for a, b in zip(want, got):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert b200_lib.lib.copy_SIFT3D(C.byref(g.s), C.byref(c.s)) == 0
+        for a, b in zip(want, host_levels(c)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        # a second detect on another size drops the stale host copies
+        g.detect_keypoints(blob_volume((32, 36, 40), seed=2))
+        assert not bool(g.s.gpyr.levels[0].data)
+
+
 def test_full_size_properties(b200_lib):
     """Size-independent properties at a size the CPU oracle cannot do in seconds (256^3):
     determinism, scan order, scale invariance of the normalised input, descriptor norms."""
