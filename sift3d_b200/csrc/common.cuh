@@ -77,7 +77,8 @@ struct s3d_engine {
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
     int opt_desc_v2 = 0;  // 1: k_descriptor2 (raster-order rows) instead of k_descriptor3 (cell-owner lanes)
-    int opt_orient_stage = 0;  // 1: k_orient_stage (experimental, unmeasured) instead of k_orient
+    int opt_orient_scalar = 0;  // 1: k_orient_group reads the level (7 loads) instead of the gradient volume
+    int opt_orient_v1 = 0;  // 1: thread-per-candidate k_orient instead of k_orient_group (A/B, tests)
     int ori_max_twx = 0;       // widest weight-table row of the current orientation tables
     int opt_orient_batch = 4;  // voxels k_orient fetches ahead (4, or 8 = line-aligned batches)
     int opt_desc_norot = 0;  // 1: no lane-dependent vertex order in k_descriptor2 (A/B only)
@@ -122,6 +123,7 @@ struct s3d_engine {
     // 16-byte gather per voxel instead of six 4-byte ones.  Optional (nullptr: scalar path).
     std::vector<float4 *> grad;        // per gpyr level
     std::vector<size_t> grad_cap;      // voxels allocated
+    std::vector<float4 *> grad_uploaded;  // what d_level_gptrs currently holds
     float4 **d_level_gptrs = nullptr;  // device table (nullptr entries allowed)
     bool grad_valid = false;           // volumes match the current pyramid contents
 
@@ -130,6 +132,10 @@ struct s3d_engine {
     size_t ori_pool_cap = 0;
     void *d_ori_tabs = nullptr;
     size_t ori_tabs_cap = 0;
+    void *d_ori_lists = nullptr;   // in-sphere offset lists (same offsets as the pool)
+    bool ori_lists_ok = false;
+    std::vector<double> ori_key;   // scales / units the tables were built for
+    int ori_key_rc = 1;
 
     // dense-descriptor buffers (raw, smoothed, 12-channel temp, 12-channel result), kept between
     // calls, and the pinned staging ring of the pageable-destination download

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 
 static thread_local std::string g_create_err;
@@ -169,7 +170,6 @@ int s3d_engine_create(s3d_engine **out, int device)
     if (const char *v = getenv("S3D_DESC_OCC")) e->opt_desc_occ = atoi(v);
     if (const char *v = getenv("S3D_DESC_NOROT")) e->opt_desc_norot = atoi(v);
     if (const char *v = getenv("S3D_ORIENT_BATCH")) e->opt_orient_batch = atoi(v);
-    if (const char *v = getenv("S3D_ORIENT_STAGE")) e->opt_orient_stage = atoi(v);
     if ((ce = cudaMalloc(&e->d_counter, 4 * sizeof(int))) != cudaSuccess) {
         s3d_fail(nullptr, "cudaMalloc", ce, __FILE__, __LINE__);
         cudaStreamDestroy(e->own_stream);
@@ -188,7 +188,7 @@ void s3d_engine_destroy(s3d_engine *e)
     free_pyramid(e);
     void *ptrs[] = {e->im,    e->scratch[0], e->scratch[1], e->d_cand,  e->d_mask, e->d_blockcnt,
                     e->d_counter, e->d_kp_all, e->d_ok,       e->d_pos,   e->d_kp,   e->d_kp_in,
-                    e->d_desc, e->d_mesh, e->d_blur_dbg, e->d_ori_pool, e->d_ori_tabs};
+                    e->d_desc, e->d_mesh, e->d_blur_dbg, e->d_ori_pool, e->d_ori_tabs, e->d_ori_lists};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &t : e->segtabs)
@@ -244,7 +244,8 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
     else if (!strcmp(name, "desc_norot")) e->opt_desc_norot = value;
     else if (!strcmp(name, "orient_batch")) e->opt_orient_batch = value;
-    else if (!strcmp(name, "orient_stage")) e->opt_orient_stage = value;
+    else if (!strcmp(name, "orient_v1")) e->opt_orient_v1 = value;
+    else if (!strcmp(name, "orient_scalar")) e->opt_orient_scalar = value;
     else if (!strcmp(name, "blur_dbg")) {
         DeviceGuard guard(e->device);
         if (value && !e->d_blur_dbg) {
@@ -764,21 +765,88 @@ static int stage_ensure(s3d_engine *e, size_t bytes)
     return 0;
 }
 
-// memcpy by a team of up to 8 host threads (page-aligned shares)
-static void par_memcpy(char *d, const char *src, size_t len)
-{
-    unsigned nthr = std::thread::hardware_concurrency();
-    nthr = nthr < 1 ? 1 : (nthr > 8 ? 8 : nthr);
-    const size_t part = ((len + nthr - 1) / nthr + 4095) & ~(size_t)4095;
-    std::vector<std::thread> team;
-    for (unsigned t = 1; t < nthr; t++) {
-        const size_t lo = t * part;
-        if (lo >= len) break;
-        team.emplace_back([=] { memcpy(d + lo, src + lo, std::min(part, len - lo)); });
+// A persistent team of host threads for the staged copies to / from pageable memory (creating
+// threads per 32 MB chunk cost ~3 ms per 512 MB volume).  One team per process, created on
+// first use; its size is the core count divided by the ranks sharing the host
+// ($LOCAL_WORLD_SIZE, set by torchrun), at most 8 ($S3D_COPY_THREADS overrides).
+namespace {
+class HostTeam {
+public:
+    static HostTeam &get()
+    {
+        static HostTeam t;
+        return t;
     }
-    memcpy(d, src, std::min(part, len));
-    for (auto &th : team) th.join();
-}
+    // memcpy split into page-aligned shares; the caller takes share 0
+    void copy(char *d, const char *src, size_t len)
+    {
+        std::unique_lock<std::mutex> lk(call_mu_);  // one copy at a time (engines share the team)
+        const unsigned n = (unsigned)workers_.size() + 1;
+        const size_t part = ((len + n - 1) / n + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            d_ = d, s_ = src, len_ = len, part_ = part;
+            pending_ = (int)workers_.size();
+            gen_++;
+        }
+        cv_.notify_all();
+        memcpy(d, src, std::min(part, len));
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [&] { return pending_ == 0; });
+    }
+
+private:
+    HostTeam()
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw < 1) hw = 1;
+        unsigned share = 1;
+        if (const char *v = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(v));
+        unsigned n = std::max(2u, std::min(8u, hw / share));  // measured on a 16-core host: 8 beats 16
+        if (const char *v = getenv("S3D_COPY_THREADS")) n = (unsigned)std::max(1, atoi(v));
+        for (unsigned t = 1; t < n; t++) workers_.emplace_back([this, t] { run(t); });
+    }
+    ~HostTeam()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+    }
+    void run(unsigned t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> g(mu_);
+            cv_.wait(g, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            char *d = d_;
+            const char *s = s_;
+            const size_t len = len_, part = part_;
+            g.unlock();
+            const size_t lo = (size_t)t * part;
+            if (lo < len) memcpy(d + lo, s + lo, std::min(part, len - lo));
+            g.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+    char *d_ = nullptr;
+    const char *s_ = nullptr;
+    size_t len_ = 0, part_ = 0;
+};
+}  // namespace
+
+static void par_memcpy(char *d, const char *src, size_t len) { HostTeam::get().copy(d, src, len); }
 
 // Device -> PAGEABLE host memory (the caller's malloc'ed Image, SURVEY.md 8b ownership rule).
 // A plain cudaMemcpy stages through the driver's bounce buffer and copies out on one core; here
@@ -821,7 +889,7 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
 // buffer while the DMA drains the other.
 static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes)
 {
-    const size_t CH = (size_t)32 << 20;
+    const size_t CH = (size_t)16 << 20;
     if (!e->opt_dense_copy || bytes < 2 * CH) {
         S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
         return 0;

@@ -142,6 +142,87 @@ __device__ __forceinline__ int icos_bin_t(const FA &F, const float g[3], float b
     return -1;
 }
 
+// Face constants padded to 20 words (80 bytes) in shared memory: a face is fetched with four
+// 16-byte loads instead of sixteen 4-byte ones.  Word k: e1 0-2, e2 3-5, t 6-8, q 9-11, e2q 12,
+// vertex byte offsets 13-15 (k_descriptor3 rewrites the indices).
+struct FaceSh4 {
+    unsigned fa, la;  // shared-window byte addresses of the padded face array and of the lut
+    __device__ __forceinline__ void load(int face, float4 v[4]) const
+    {
+        const unsigned a = fa + 80u * (unsigned)face;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+            : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[0].z), "=f"(v[0].w) : "r"(a));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];"
+            : "=f"(v[1].x), "=f"(v[1].y), "=f"(v[1].z), "=f"(v[1].w) : "r"(a));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];"
+            : "=f"(v[2].x), "=f"(v[2].y), "=f"(v[2].z), "=f"(v[2].w) : "r"(a));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+48];"
+            : "=f"(v[3].x), "=f"(v[3].y), "=f"(v[3].z), "=f"(v[3].w) : "r"(a));
+    }
+    __device__ __forceinline__ int lut(int i) const
+    {
+        int v;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(la + 4u * (unsigned)i));
+        return v;
+    }
+};
+
+// face_test on a face already in registers (same arithmetic, same order)
+__device__ __forceinline__ bool face_test4(const float4 v[4], const float g[3], float bary[3])
+{
+    const float e10 = v[0].x, e11 = v[0].y, e12 = v[0].z, e20 = v[0].w, e21 = v[1].x, e22 = v[1].y;
+    const float t0 = v[1].z, t1 = v[1].w, t2 = v[2].x, q0 = v[2].y, q1 = v[2].z, q2 = v[2].w;
+    float p[3];
+    p[0] = fs(fm(g[1], e22), fm(g[2], e21));
+    p[1] = fs(fm(g[2], e20), fm(g[0], e22));
+    p[2] = fs(fm(g[0], e21), fm(g[1], e20));
+    const float det = dot3(e10, p[0], e11, p[1], e12, p[2]);
+    if ((double)fabsf(det) < K_BARY_EPS) return false;
+    const float det_inv = __fdiv_rn(1.0f, det);
+    bary[1] = fm(det_inv, dot3(t0, p[0], t1, p[1], t2, p[2]));
+    bary[2] = fm(det_inv, dot3(g[0], q0, g[1], q1, g[2], q2));
+    bary[0] = fs(fs(1.0f, bary[1]), bary[2]);
+    const float k = fm(v[3].x, det_inv);
+    return !((double)bary[0] < -K_BARY_EPS || (double)bary[1] < -K_BARY_EPS ||
+             (double)bary[2] < -K_BARY_EPS || k < 0.0f);
+}
+
+// icos_bin_t on the padded table; also returns words 13-15 of the chosen face
+template <bool FAST>
+__device__ __forceinline__ int icos_bin4(const FaceSh4 &F, const float g[3], float bary[3], int voff[3])
+{
+    const float n2 = fa(fa(fm(g[0], g[0]), fm(g[1], g[1])), fm(g[2], g[2]));
+    if ((double)n2 < K_BARY_EPS) return -1;
+    float4 v[4];
+    if (FAST) {
+        const float ax = fabsf(g[0]), ay = fabsf(g[1]), az = fabsf(g[2]);
+        const float PHI = 1.6180339887f, IPH = 0.6180339887f;
+        const float s0 = ax + ay + az, s1 = ax * IPH + az * PHI, s2 = ax * PHI + ay * IPH,
+                    s3 = ay * PHI + az * IPH;
+        int type = 0;
+        float bs = s0;
+        if (s1 > bs) bs = s1, type = 1;
+        if (s2 > bs) bs = s2, type = 2;
+        if (s3 > bs) bs = s3, type = 3;
+        const int sb = (g[0] < 0.0f ? 1 : 0) | (g[1] < 0.0f ? 2 : 0) | (g[2] < 0.0f ? 4 : 0);
+        const int best = F.lut(type * 8 + sb);
+        const float margin = 1e-4f;
+        F.load(best, v);
+        if (face_test4(v, g, bary) && bary[0] > margin && bary[1] > margin && bary[2] > margin) {
+            voff[0] = __float_as_int(v[3].y), voff[1] = __float_as_int(v[3].z), voff[2] = __float_as_int(v[3].w);
+            return best;
+        }
+    }
+    for (int i = 0; i < 20; i++) {
+        F.load(i, v);
+        if (face_test4(v, g, bary)) {
+            voff[0] = __float_as_int(v[3].y), voff[1] = __float_as_int(v[3].z), voff[2] = __float_as_int(v[3].w);
+            return i;
+        }
+    }
+    return -1;
+}
+
 __device__ __forceinline__ int icos_bin(const FaceConst *F /* shared memory */, const int *lut,
                                         const float g[3], float bary[3], const bool fast = true)
 {
@@ -437,8 +518,10 @@ __device__ __forceinline__ bool orient_core(const float *__restrict__ im, int nx
 // with exactly the arithmetic of orient_core (-1 marks offsets outside the sphere), which takes
 // the f64 division and the exp out of the per-candidate loop.
 struct OriTab {
-    int off;  // first entry in the table pool, -1 if the level has none
+    int off;  // first entry in the table pool (and in the list pool), -1 if the level has none
     int rx, ry, rz;
+    int list_n;  // entries of the level's in-sphere offset list (k_orient_list)
+    int pad[3];
 };
 
 __global__ void __launch_bounds__(256)
@@ -588,122 +671,189 @@ __global__ void __launch_bounds__(128, TAB ? (BATCH == 8 ? 6 : 8) : 4)
     if (conf_out) conf_out[i] = conf;
 }
 
-// EXPERIMENTAL (option "orient_stage", default off; written at the end of round 1 without GPU
-// time left to measure it).  Same per-candidate arithmetic in the same order as k_orient<true>,
-// but the 32 candidates of a warp walk their windows in LOCKSTEP over the offset (dz, dy):
-//   * the weight row of an offset is the same for all of them (same level, integer centres):
-//     ONE coalesced load, its sphere chord [jlo, jhi] by ballot, rows without a chord skipped;
-//   * the 32 gradient rows are fetched COOPERATIVELY, one candidate's row per step with lanes
-//     = consecutive voxels (one coalesced request of <= 27 x 16 B instead of 27 requests of 32
-//     scattered sectors each), into a per-warp shared tile of odd pitch (LDS.128 conflict-free);
-//   * each lane then consumes ITS row from shared memory in ascending x -- the f32 window
-//     gradient and the f64 tensor sums see exactly the reference's sequence.
-// A warp whose candidates do not share one level (the seams of the candidate list), or whose
-// level has no gradient volume, takes the per-thread path.
-#define ORI_STAGE_WARPS 2
-__global__ void __launch_bounds__(32 * ORI_STAGE_WARPS)
-    k_orient_stage(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
+// ---- grouped orientation kernel (the default) -----------------------------------------------
+// Eight lanes per candidate, four candidates per warp.  The in-sphere offsets of a level are a
+// LIST in the reference's raster order (k_orient_list compacts the weight table), so a group
+// walks 8 consecutive list entries per step: no sphere test, every lane busy, and the 8
+// gradient fetches of a group are consecutive voxels of a row -- one 128-byte line instead of
+// the 8 scattered sectors of the thread-per-candidate kernel, which is bound by that latency.
+//   * The f32 window gradient (vd_win, sift.c:1416-1417) decides accept / reject through the
+//     corner score, and a re-associated sum moves it by 1e-7 -- about one flipped candidate in
+//     two 512^3 volumes.  It is therefore summed in the reference's exact order: the lanes
+//     leave their terms g * w in shared memory and lanes 0..2 of the group add the eight terms
+//     of "their" component one after the other (voxels outside the volume, which the
+//     reference's clamped loop bounds skip, add an exact +0).
+//   * The f64 structure tensor is order-insensitive at the 1e-16 level (its eigenvectors are
+//     rounded to f32, and no decision sits within 1e-15 of its threshold): per-lane partial
+//     sums, combined with a 3-step butterfly.
+#define ORI_G 8
+#define ORI_WARPS 4
+// SCALAR: central differences from the level itself (7 x 4-byte loads, 4 bytes of footprint per
+// voxel) instead of the float4 gradient volume (one 16-byte load, 16 bytes of footprint)
+template <bool SCALAR>
+__global__ void __launch_bounds__(32 * ORI_WARPS)
+    k_orient_group(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
                    double corner_thresh, unsigned char *__restrict__ ok,
-                   const OriTab *__restrict__ tabs, const float *__restrict__ pool, int pitch)
+                   const OriTab *__restrict__ tabs, const int2 *__restrict__ lists)
 {
-    extern __shared__ float4 s_rows4[];
+    __shared__ __align__(16) float s_t[ORI_WARPS][32 / ORI_G][3][ORI_G];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *tile = s_rows4 + (size_t)warp * 32 * pitch;
-    const int i = (blockIdx.x * ORI_STAGE_WARPS + warp) * 32 + lane;
+    const int grp = lane / ORI_G, gl = lane % ORI_G;
+    const int i = (blockIdx.x * ORI_WARPS + warp) * (32 / ORI_G) + grp;
     const bool valid = i < n;
     s3d_keypoint c;
-    c.o = 0, c.s = 0, c.x = c.y = c.z = 0.0f, c.sd = 1.0;
+    c.o = 0, c.s = T.first_level, c.x = c.y = c.z = 0.0f, c.sd = 1.0;
     if (valid) c = kps[i];
-    const int lv = valid ? c.o * T.nlev_g + (c.s - T.first_level) : -1;
-    // one level for the whole warp?
-    const int lv0 = __shfl_sync(0xffffffffu, lv, 0);
-    const bool uniform = __all_sync(0xffffffffu, !valid || lv == lv0) && lv0 >= 0 && T.gptrs &&
-                         T.gptrs[lv0] != nullptr;
-    float R[9];
-    double conf = 0.0;
-    bool accept = false;
-    if (!uniform) {  // per-thread path (warp-uniform branch)
-        if (valid) {
-            const float zl = local_z(T, lv, c.z);
-            accept = orient_core_tab<4>(T.ptrs[lv], T.dims[3 * lv], T.dims[3 * lv + 1],
-                                        T.dims[3 * lv + 2], T.units[3 * lv], T.units[3 * lv + 1],
-                                        T.units[3 * lv + 2], (int)c.x, (int)c.y, (int)zl,
-                                        sig_fctr * c.sd, pool + tabs[lv].off, tabs[lv],
-                                        T.gptrs ? T.gptrs[lv] : nullptr, corner_thresh, R, conf);
-        }
-    } else {
-        const int L = lv0;
-        const OriTab t = tabs[L];
-        const int nx = T.dims[3 * L], ny = T.dims[3 * L + 1], nz = T.dims[3 * L + 2];
-        const float uxf = T.units[3 * L], uyf = T.units[3 * L + 1], uzf = T.units[3 * L + 2];
-        const float4 *__restrict__ gim = T.gptrs[L];
-        const float *__restrict__ tab = pool + t.off;
-        const long long nvox = (long long)nx * ny * nz;
-        const int cx = (int)c.x, cy = (int)c.y, cz = (int)local_z(T, L, c.z);
-        const double win_radius = sig_fctr * c.sd * 3.0;
-        int x0 = 0, x1 = -1, y0 = 0, y1 = -1, z0 = 0, z1 = -1;
-        if (valid) {  // bounds exactly as orient_core_tab
-            sphere_bounds_d((float)cx, win_radius, uxf, nx, x0, x1);
-            sphere_bounds_d((float)cy, win_radius, uyf, ny, y0, y1);
-            sphere_bounds_d((float)cz, win_radius, uzf, nz, z0, z1);
-            x0 = max(x0, cx - t.rx), x1 = min(x1, cx + t.rx);
-            y0 = max(y0, cy - t.ry), y1 = min(y1, cy + t.ry);
-            z0 = max(z0, cz - t.rz), z1 = min(z1, cz + t.rz);
-        }
-        const long long ys = nx, zs = (long long)nx * ny;
-        const int twx = 2 * t.rx + 1, twy = 2 * t.ry + 1;
-        double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
-        float wx = 0.0f, wy = 0.0f, wz = 0.0f;
-        for (int dz = -t.rz; dz <= t.rz; dz++)
-            for (int dy = -t.ry; dy <= t.ry; dy++) {
-                const float *wr = tab + ((size_t)(dz + t.rz) * twy + (dy + t.ry)) * twx;
-                const float wreg = lane < twx ? __ldg(wr + lane) : -1.0f;
-                const unsigned inside = __ballot_sync(0xffffffffu, wreg >= 0.0f);
-                if (!inside) continue;  // the row misses the sphere (warp-uniform)
-                const int jlo = __ffs(inside) - 1, jhi = 31 - __clz(inside);
-                const int z = cz + dz, y = cy + dy;
-                const bool rowact = valid && z >= z0 && z <= z1 && y >= y0 && y <= y1;
-                const unsigned act = __ballot_sync(0xffffffffu, rowact);
-                if (!act) continue;
-                // voxel index of (cx - rx, y, z): the row this lane consumes
-                const long long ebase = (long long)z * zs + (long long)y * ys + (cx - t.rx);
-                for (unsigned m = act; m; m &= m - 1) {  // cooperative fetch, one row per step
-                    const int k = __ffs(m) - 1;
-                    const long long eb = __shfl_sync(0xffffffffu, ebase, k);
-                    if (lane >= jlo && lane <= jhi) {
-                        long long e = eb + lane;  // clamped: out-of-row voxels are never consumed
-                        e = e < 0 ? 0 : (e >= nvox ? nvox - 1 : e);
-                        tile[k * pitch + lane] = __ldg(gim + e);
+    const int lv = c.o * T.nlev_g + (c.s - T.first_level);
+    const OriTab t = tabs[lv];
+    const int nl = valid ? t.list_n : 0;
+    const int2 *__restrict__ list = lists + t.off;
+    const int nx = T.dims[3 * lv], ny = T.dims[3 * lv + 1], nz = T.dims[3 * lv + 2];
+    const float4 *__restrict__ gim = SCALAR ? nullptr : T.gptrs[lv];
+    const float *__restrict__ im = T.ptrs[lv];
+    const float iux = __fdiv_rn(1.0f, T.units[3 * lv]), iuy = __fdiv_rn(1.0f, T.units[3 * lv + 1]),
+                iuz = __fdiv_rn(1.0f, T.units[3 * lv + 2]);
+    const size_t ys = nx, zs = (size_t)nx * ny;
+    const int cx = (int)c.x, cy = (int)c.y, cz = (int)local_z(T, lv, c.z);
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    float wsum = 0.0f;  // lanes 0..2 of the group: x, y, z component of the window gradient
+    // ORI_U batches of 8 entries per trip: all their gradient fetches are issued before the
+    // first is used (the kernel is bound by the latency of these gathers -- ncu: 11 stalled
+    // warps on the long scoreboard per issue with one batch in flight)
+    constexpr int ORI_U = 4;
+    const int nit = __reduce_max_sync(0xffffffffu, (nl + ORI_U * ORI_G - 1) / (ORI_U * ORI_G));
+    float *const st = &s_t[warp][grp][0][0];
+    for (int it = 0; it < nit; it++) {
+        float4 g[ORI_U];
+        float w[ORI_U];
+#pragma unroll
+        for (int k = 0; k < ORI_U; k++) {
+            const int e = (it * ORI_U + k) * ORI_G + gl;
+            w[k] = -1.0f;  // no voxel
+            g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < nl) {
+                const int2 ent = __ldg(list + e);
+                const int x = cx + (int)(signed char)(ent.x & 0xff), y = cy + (int)(signed char)((ent.x >> 8) & 0xff),
+                          z = cz + (int)(signed char)((ent.x >> 16) & 0xff);
+                // IM_LOOP_SPHERE_START clamps the loops to [1, n - 2] (sift.c:96-119)
+                if ((unsigned)(x - 1) <= (unsigned)(nx - 3) && (unsigned)(y - 1) <= (unsigned)(ny - 3) &&
+                    (unsigned)(z - 1) <= (unsigned)(nz - 3)) {
+                    w[k] = __int_as_float(ent.y);
+                    const size_t idx = ((size_t)z * ny + y) * nx + x;
+                    if (SCALAR) {  // SIFT3D_IM_GET_GRAD (immacros.h:105) / units, as k_gradient
+                        const float *p = im + idx;
+                        g[k].x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+                        g[k].y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+                        g[k].z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+                    } else {
+                        g[k] = __ldg(gim + idx);
                     }
                 }
-                __syncwarp();
-                for (int j = jlo; j <= jhi; j++) {
-                    const float w = __shfl_sync(0xffffffffu, wreg, j);
-                    const int x = cx - t.rx + j;
-                    if (rowact && w >= 0.0f && x >= x0 && x <= x1) {
-                        const float4 g = tile[lane * pitch + j];
-                        const double dw = (double)w, gxd = g.x, gyd = g.y, gzd = g.z;
-                        a00 = __dadd_rn(a00, __dmul_rn(__dmul_rn(gxd, gxd), dw));
-                        a01 = __dadd_rn(a01, __dmul_rn(__dmul_rn(gxd, gyd), dw));
-                        a02 = __dadd_rn(a02, __dmul_rn(__dmul_rn(gxd, gzd), dw));
-                        a11 = __dadd_rn(a11, __dmul_rn(__dmul_rn(gyd, gyd), dw));
-                        a12 = __dadd_rn(a12, __dmul_rn(__dmul_rn(gyd, gzd), dw));
-                        a22 = __dadd_rn(a22, __dmul_rn(__dmul_rn(gzd, gzd), dw));
-                        wx = fa(wx, fm(g.x, w));
-                        wy = fa(wy, fm(g.y, w));
-                        wz = fa(wz, fm(g.z, w));
-                    }
-                }
-                __syncwarp();
             }
-        if (valid)
-            accept = orient_finish(a00, a01, a02, a11, a12, a22, wx, wy, wz, corner_thresh, R, conf);
+        }
+#pragma unroll
+        for (int k = 0; k < ORI_U; k++) {
+            float tx = 0.0f, ty = 0.0f, tz = 0.0f;
+            if (w[k] >= 0.0f) {
+                const double dw = (double)w[k], gxd = g[k].x, gyd = g[k].y, gzd = g[k].z;
+                a00 = __dadd_rn(a00, __dmul_rn(__dmul_rn(gxd, gxd), dw));
+                a01 = __dadd_rn(a01, __dmul_rn(__dmul_rn(gxd, gyd), dw));
+                a02 = __dadd_rn(a02, __dmul_rn(__dmul_rn(gxd, gzd), dw));
+                a11 = __dadd_rn(a11, __dmul_rn(__dmul_rn(gyd, gyd), dw));
+                a12 = __dadd_rn(a12, __dmul_rn(__dmul_rn(gyd, gzd), dw));
+                a22 = __dadd_rn(a22, __dmul_rn(__dmul_rn(gzd, gzd), dw));
+                tx = fm(g[k].x, w[k]);
+                ty = fm(g[k].y, w[k]);
+                tz = fm(g[k].z, w[k]);
+            }
+            st[gl] = tx;
+            st[ORI_G + gl] = ty;
+            st[2 * ORI_G + gl] = tz;
+            __syncwarp();
+            if (gl < 3) {  // the reference's order: voxel after voxel (sift.c:1416-1417)
+                const float4 v0 = *reinterpret_cast<const float4 *>(st + ORI_G * gl);
+                const float4 v1 = *reinterpret_cast<const float4 *>(st + ORI_G * gl + 4);
+                wsum = fa(wsum, v0.x);
+                wsum = fa(wsum, v0.y);
+                wsum = fa(wsum, v0.z);
+                wsum = fa(wsum, v0.w);
+                wsum = fa(wsum, v1.x);
+                wsum = fa(wsum, v1.y);
+                wsum = fa(wsum, v1.z);
+                wsum = fa(wsum, v1.w);
+            }
+            __syncwarp();
+        }
     }
-    if (valid) {
+#pragma unroll
+    for (int o = 1; o < ORI_G; o <<= 1) {
+        a00 = __dadd_rn(a00, __shfl_xor_sync(0xffffffffu, a00, o));
+        a01 = __dadd_rn(a01, __shfl_xor_sync(0xffffffffu, a01, o));
+        a02 = __dadd_rn(a02, __shfl_xor_sync(0xffffffffu, a02, o));
+        a11 = __dadd_rn(a11, __shfl_xor_sync(0xffffffffu, a11, o));
+        a12 = __dadd_rn(a12, __shfl_xor_sync(0xffffffffu, a12, o));
+        a22 = __dadd_rn(a22, __shfl_xor_sync(0xffffffffu, a22, o));
+    }
+    const float wx = __shfl_sync(0xffffffffu, wsum, grp * ORI_G + 0);
+    const float wy = __shfl_sync(0xffffffffu, wsum, grp * ORI_G + 1);
+    const float wz = __shfl_sync(0xffffffffu, wsum, grp * ORI_G + 2);
+    if (valid && gl == 0) {
+        float R[9];
+        double conf;
+        const bool accept = orient_finish(a00, a01, a02, a11, a12, a22, wx, wy, wz, corner_thresh, R, conf);
 #pragma unroll
         for (int k = 0; k < 9; k++) kps[i].R[k] = R[k];
         ok[i] = accept ? 1 : 0;
     }
+}
+
+// In-sphere offsets of every level's weight table, in raster order: {dx | dy << 8 | dz << 16
+// (signed bytes), weight bits}.  One block per level; ordered compaction chunk by chunk.
+__global__ void __launch_bounds__(1024)
+    k_orient_list(OriTab *__restrict__ tabs, const float *__restrict__ pool, int2 *__restrict__ lists)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    OriTab t = tabs[blockIdx.x];
+    if (t.off < 0) return;
+    const int wx = 2 * t.rx + 1, wy = 2 * t.ry + 1, wz = 2 * t.rz + 1;
+    const int tot = wx * wy * wz;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < tot; base += 1024) {
+        const int i = base + threadIdx.x;
+        const float w = i < tot ? pool[t.off + i] : -1.0f;
+        const int v = w >= 0.0f ? 1 : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += u;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int ws = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, ws, o);
+                if (threadIdx.x >= o) ws += u;
+            }
+            s_warp[threadIdx.x] = ws;
+        }
+        __syncthreads();
+        const int warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+        const int run = s_run;
+        if (v) {
+            const int ix = i % wx - t.rx, iy = (i / wx) % wy - t.ry, iz = i / (wx * wy) - t.rz;
+            lists[t.off + run + warp_off + incl - 1] =
+                make_int2((ix & 0xff) | ((iy & 0xff) << 8) | ((iz & 0xff) << 16), __float_as_int(w));
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = run + warp_off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tabs[blockIdx.x].list_n = s_run;
 }
 
 // ordered compaction of accepted candidates (sift.c:1306-1324)
@@ -1514,7 +1664,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
 struct D3Smem {
     unsigned h[12 * D3_VSTRIDE];
     unsigned long long tab[32];
-    FaceConst face[20];  // idx[] rewritten to byte offsets of the vertex planes
+    float4 face[20][5];  // FaceConst padded to 80 bytes; words 13-15 = byte offsets of the vertex planes
     int lut[32];
     float kc[4];  // r2, s2
     D3Scan scan;  // row-scan constants of the keypoint
@@ -1585,7 +1735,7 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
     unsigned sb = (unsigned)__cvta_generic_to_shared(&S);
     asm volatile("" : "+r"(sb));  // opaque: one base register for all shared data (see k_descriptor2)
     const unsigned h_addr = sb + (unsigned)offsetof(D3Smem, h);
-    const FaceSh faces{sb + (unsigned)offsetof(D3Smem, face), sb + (unsigned)offsetof(D3Smem, lut)};
+    const FaceSh4 faces{sb + (unsigned)offsetof(D3Smem, face), sb + (unsigned)offsetof(D3Smem, lut)};
     const TabSh etab{sb + (unsigned)offsetof(D3Smem, tab)};
     const unsigned kc_addr = sb + (unsigned)offsetof(D3Smem, kc);
     const int ki = blockIdx.x;
@@ -1626,7 +1776,13 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         S.kc[0] = K.r2, S.kc[1] = s2;
         d3_scan_setup(K, S.scan);
     }
-    load_faces(S.face, S.lut, M);
+    if (tid < 32) S.lut[tid] = c_face_lut[tid];
+    for (int i = tid; i < 20 * 16; i += D3_THREADS) {  // 16 of the 19 words of a FaceConst
+        const int f = i >> 4, k = i & 15;
+        unsigned w = __ldg(reinterpret_cast<const unsigned *>(M->f + f) + k);
+        if (k >= 13) w *= (unsigned)(D3_VSTRIDE * 4);  // vertex index -> byte offset of its plane
+        reinterpret_cast<unsigned *>(&S.face[f][0])[k] = w;
+    }
     // Bound of the gradient magnitude over the window's bounding box, from the per-plane 8x8
     // block maxima of |g|^2 behind the gradient volume.
     float m2 = 0.0f;
@@ -1658,10 +1814,6 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         scan_done = (warp >> 1) >= nrows;
     }
     __syncthreads();
-    if (tid < 60) {  // vertex index -> byte offset of its plane
-        int *w = &S.face[tid / 3].idx[tid % 3];
-        *w = *w * (D3_VSTRIDE * 4);
-    }
 #pragma unroll
     for (int i = 0; i < D3_THREADS / 32; i++) m2 = fmaxf(m2, s_gmax[i]);
     // Fixed-point scale 2^S (block-uniform).  A contribution is mag * 2^S * w_c * bary with
@@ -1765,7 +1917,8 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         for (int a = 0; a < 3; a++)
             gr[a] = dot3(K.Rt[3 * a], g[0], K.Rt[3 * a + 1], g[1], K.Rt[3 * a + 2], g[2]);
         float bary[3];
-        const int bin = icos_bin_t(faces, gr, bary, FAST);
+        int voff[3];
+        const int bin = icos_bin4<FAST>(faces, gr, bary, voff);
         if (bin < 0) continue;
         const float mag = __fsqrt_rn(fa(fa(fm(gr[0], gr[0]), fm(gr[1], gr[1])), fm(gr[2], gr[2])));
         // The scatter (sift.c:1763-1765: (mag * w_c) * bary_j into the 8 cells x 3 vertices) in
@@ -1775,9 +1928,9 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         // magic constant (the float-to-int conversion is a quarter-rate instruction, and there
         // are 24 per voxel): 12 FFMA2 instead of 32 FMUL + 24 F2I.
         const float mag_s = fm(mag, mag_scale);
-        const unsigned va0 = cell_addr + (unsigned)faces.idx<0>(bin);
-        const unsigned va1 = cell_addr + (unsigned)faces.idx<1>(bin);
-        const unsigned va2 = cell_addr + (unsigned)faces.idx<2>(bin);
+        const unsigned va0 = cell_addr + (unsigned)voff[0];
+        const unsigned va1 = cell_addr + (unsigned)voff[1];
+        const unsigned va2 = cell_addr + (unsigned)voff[2];
         const float wx0 = fs(1.0f, dv[0]), wy0 = fs(1.0f, dv[1]), wz0 = fs(1.0f, dv[2]);
         const u64x mb01 = mul2x(pk2(mag_s, mag_s), pk2(bary[0], bary[1]));
         const float mb2 = fm(mag_s, bary[2]);
@@ -2044,37 +2197,38 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     k_gradient(const float *__restrict__ im, int nx, int ny, int nz, float iux, float iuy,
                float iuz, float4 *__restrict__ out, float *__restrict__ bmax, int nbx, int nby)
-{   // grid: (ceil(nx / 32), ceil(ny / 8), nz), block (32, 8): one voxel per thread, no index
-    // division.  Also leaves max |g|^2 over every 8 x 8 x 1 block of voxels in bmax[z][y/8][x/8]
-    // (k_descriptor3 bounds the gradient magnitude inside a window with it).
-    __shared__ float s_m[8][4];
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, z = blockIdx.z;
+{   // grid: (ceil(nx / 32), ceil(ny / 8), ceil(nz / 8)), block 256: warp w owns plane
+    // 8 * blockIdx.z + w and walks the 8 rows of its y block, lanes along x (512-byte stores).
+    // Also leaves max |g|^2 over every 8 x 8 x 1 block of voxels in bmax[z][y/8][x/8]
+    // (k_descriptor3 bounds the gradient magnitude inside a window with it): a register max
+    // over the rows, then a 3-step butterfly over the 8 lanes of an x block -- no shared memory.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane, z = blockIdx.z * 8 + warp;
+    if (z >= nz) return;
+    const size_t ys = nx, zs = (size_t)nx * ny;
     float m2 = 0.0f;
-    if (x < nx && y < ny) {
-        const size_t ys = nx, zs = (size_t)nx * ny;
-        const size_t idx = x + y * ys + z * zs;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
-            const float *p = im + idx;
-            g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
-            g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
-            g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+    const bool xin = x >= 1 && x <= nx - 2, zin = z >= 1 && z <= nz - 2;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int y = blockIdx.y * 8 + r;
+        if (x < nx && y < ny) {
+            const size_t idx = x + y * ys + z * zs;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xin && zin && y >= 1 && y <= ny - 2) {
+                const float *p = im + idx;
+                g.x = fm(fm(0.5f, fs(__ldg(p + 1), __ldg(p - 1))), iux);
+                g.y = fm(fm(0.5f, fs(__ldg(p + ys), __ldg(p - ys))), iuy);
+                g.z = fm(fm(0.5f, fs(__ldg(p + zs), __ldg(p - zs))), iuz);
+            }
+            out[idx] = g;
+            m2 = fmaxf(m2, g.x * g.x + g.y * g.y + g.z * g.z);
         }
-        out[idx] = g;
-        m2 = g.x * g.x + g.y * g.y + g.z * g.z;
     }
     m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
     m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
     m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 4));
-    if ((threadIdx.x & 7) == 0) s_m[threadIdx.y][threadIdx.x >> 3] = m2;
-    __syncthreads();
-    if (threadIdx.y == 0 && threadIdx.x < 4) {
-        float m = s_m[0][threadIdx.x];
-#pragma unroll
-        for (int r = 1; r < 8; r++) m = fmaxf(m, s_m[r][threadIdx.x]);
-        const int bxi = blockIdx.x * 4 + threadIdx.x;
-        if (bxi < nbx) bmax[((size_t)z * nby + blockIdx.y) * nbx + bxi] = m;
-    }
+    const int bxi = blockIdx.x * 4 + (lane >> 3);
+    if ((lane & 7) == 0 && bxi < nbx) bmax[((size_t)z * nby + blockIdx.y) * nbx + bxi] = m2;
 }
 
 PyrTable make_table(const s3d_engine *e)
@@ -2099,6 +2253,7 @@ void s3d_gradients_free(s3d_engine *e)
         if (p) cudaFree(p);
     e->grad.clear();
     e->grad_cap.clear();
+    e->grad_uploaded.clear();
     if (e->d_level_gptrs) cudaFree(e->d_level_gptrs);
     e->d_level_gptrs = nullptr;
     e->grad_valid = false;
@@ -2136,21 +2291,25 @@ int s3d_gradients_prepare(s3d_engine *e)
             e->grad_cap[lv] = l.n();
         }
         const float ux = (float)l.g.ux, uy = (float)l.g.uy, uz = (float)l.g.uz;
-        if (l.g.ny > 65535 || l.g.nz > 65535 || l.n() >= ((size_t)1 << 32)) {  // grid limits, 32-bit voxel index: scalar path
+        if (l.g.ny > 8 * 65535 || l.g.nz > 8 * 65535 || l.g.ny > 65535 || l.g.nz > 65535 ||
+            l.n() >= ((size_t)1 << 32)) {  // grid limits, 16-bit row records, 32-bit voxel index: scalar path
             cudaFree(e->grad[lv]);
             e->grad[lv] = nullptr;
             e->grad_cap[lv] = 0;
             continue;
         }
         const int nbx = (l.g.nx + 7) / 8, nby = (l.g.ny + 7) / 8;
-        k_gradient<<<dim3((l.g.nx + 31) / 32, nby, l.g.nz), dim3(32, 8), 0, e->stream>>>(
+        k_gradient<<<dim3((l.g.nx + 31) / 32, nby, (l.g.nz + 7) / 8), 256, 0, e->stream>>>(
             l.d, l.g.nx, l.g.ny, l.g.nz, __fdiv_rn_host(ux), __fdiv_rn_host(uy), __fdiv_rn_host(uz),
             e->grad[lv], reinterpret_cast<float *>(e->grad[lv] + l.n()), nbx, nby);
         S3D_LAUNCH_CHECK(e);
     }
-    S3D_CUDA(e, cudaMemcpyAsync(e->d_level_gptrs, e->grad.data(), L * sizeof(float4 *),
-                                cudaMemcpyHostToDevice, e->stream));
-    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->grad_uploaded != e->grad) {  // the device table only changes when a volume was (re)allocated
+        S3D_CUDA(e, cudaMemcpyAsync(e->d_level_gptrs, e->grad.data(), L * sizeof(float4 *),
+                                    cudaMemcpyHostToDevice, e->stream));
+        S3D_CUDA(e, cudaStreamSynchronize(e->stream));  // e->grad is host memory that may change
+        e->grad_uploaded = e->grad;
+    }
     e->grad_valid = true;
     return 0;
 }
@@ -2238,13 +2397,29 @@ int s3d_k_orient_list(s3d_engine *e, s3d_keypoint *d_kp, int n, double sig_fctr,
 static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr)
 {
     const int L = e->noct * e->nlev_g;
+    {   // tables and lists depend on the levels' scales and units only: keep them between calls
+        std::vector<double> key;
+        key.push_back(sig_fctr);
+        key.push_back((double)e->K);
+        key.push_back((double)e->first_level);
+        for (int lv = 0; lv < L; lv++) {
+            const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
+            key.push_back(g.scale), key.push_back(g.ux), key.push_back(g.uy), key.push_back(g.uz);
+        }
+        if (e->d_ori_tabs && key == e->ori_key) return e->ori_key_rc;
+        e->ori_key = key;
+        e->ori_key_rc = 1;
+    }
     std::vector<OriTab> tabs(L);
     size_t total = 0;
     e->ori_max_twx = 0;
+    e->ori_lists_ok = true;
     for (int lv = 0; lv < L; lv++) {
         OriTab &t = tabs[lv];
         t.off = -1;
         t.rx = t.ry = t.rz = 0;
+        t.list_n = 0;
+        t.pad[0] = t.pad[1] = t.pad[2] = 0;
         const int sidx = lv % e->nlev_g + e->first_level;  // level index s
         if (sidx < 0 || sidx >= e->K) continue;
         const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
@@ -2255,6 +2430,7 @@ static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr
         t.rx = (int)ceil(r[0]) + 1;
         t.ry = (int)ceil(r[1]) + 1;
         t.rz = (int)ceil(r[2]) + 1;
+        if (t.rx > 127 || t.ry > 127 || t.rz > 127) e->ori_lists_ok = false;  // offsets are signed bytes
         e->ori_max_twx = std::max(e->ori_max_twx, 2 * t.rx + 1);
         const size_t n = (size_t)(2 * t.rx + 1) * (2 * t.ry + 1) * (2 * t.rz + 1);
         if (total + n > ((size_t)1 << 27)) return 1;
@@ -2264,9 +2440,12 @@ static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr
     if (total == 0) return 1;
     if (total > e->ori_pool_cap) {
         if (e->d_ori_pool) cudaFree(e->d_ori_pool);
+        if (e->d_ori_lists) cudaFree(e->d_ori_lists);
         e->d_ori_pool = nullptr;
+        e->d_ori_lists = nullptr;
         e->ori_pool_cap = 0;
         S3D_CUDA(e, cudaMalloc(&e->d_ori_pool, total * sizeof(float)));
+        S3D_CUDA(e, cudaMalloc(&e->d_ori_lists, total * sizeof(int2)));
         e->ori_pool_cap = total;
     }
     if ((size_t)L > e->ori_tabs_cap) {
@@ -2282,6 +2461,12 @@ static int build_orient_tables(s3d_engine *e, const PyrTable &T, double sig_fctr
     k_orient_table<<<dim3(64, L), 256, 0, e->stream>>>(static_cast<const OriTab *>(e->d_ori_tabs), T,
                                                       sig_fctr, e->d_ori_pool);
     S3D_LAUNCH_CHECK(e);
+    if (e->ori_lists_ok) {
+        k_orient_list<<<L, 1024, 0, e->stream>>>(static_cast<OriTab *>(e->d_ori_tabs), e->d_ori_pool,
+                                                 static_cast<int2 *>(e->d_ori_lists));
+        S3D_LAUNCH_CHECK(e);
+    }
+    e->ori_key_rc = 0;
     return 0;
 }
 
@@ -2311,14 +2496,23 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
         const int trc = build_orient_tables(e, T, 1.5);
         if (trc < 0) return -1;
         if (trc == 0) {  // every keypoint level has a table
-            const int pitch = e->ori_max_twx | 1;
-            const size_t stage_smem = (size_t)ORI_STAGE_WARPS * 32 * pitch * sizeof(float4);
-            if (e->opt_orient_stage && pitch <= 31 && stage_smem <= 48 * 1024)
-                k_orient_stage<<<(n + 32 * ORI_STAGE_WARPS - 1) / (32 * ORI_STAGE_WARPS),
-                                 32 * ORI_STAGE_WARPS, stage_smem, e->stream>>>(
-                    e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok,
-                    static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool, pitch);
-            else if (e->opt_orient_batch == 8)
+            bool grads = e->grad_valid;
+            for (int lv = 0; grads && lv < (int)e->g.size(); lv++) {
+                const int sidx = lv % e->nlev_g + e->first_level;
+                if (sidx >= 0 && sidx < e->K && !e->grad[lv]) grads = false;
+            }
+            if (e->ori_lists_ok && !e->opt_orient_v1) {  // grouped kernel
+                const int per_cta = ORI_WARPS * (32 / ORI_G);
+                const int grid = (n + per_cta - 1) / per_cta;
+                if (grads && !e->opt_orient_scalar)
+                    k_orient_group<false><<<grid, 32 * ORI_WARPS, 0, e->stream>>>(
+                        e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok,
+                        static_cast<const OriTab *>(e->d_ori_tabs), static_cast<const int2 *>(e->d_ori_lists));
+                else
+                    k_orient_group<true><<<grid, 32 * ORI_WARPS, 0, e->stream>>>(
+                        e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok,
+                        static_cast<const OriTab *>(e->d_ori_tabs), static_cast<const int2 *>(e->d_ori_lists));
+            } else if (e->opt_orient_batch == 8)
                 k_orient<true, 8><<<(n + 127) / 128, 128, 0, e->stream>>>(
                     e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
                     static_cast<const OriTab *>(e->d_ori_tabs), e->d_ori_pool);
