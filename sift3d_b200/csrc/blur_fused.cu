@@ -96,7 +96,10 @@ struct FusedParams {
 
 enum { MODE_NORMAL = 0, MODE_STASH = 1, MODE_LERP = 2 };
 
-template <int HW>
+// AL: row length a multiple of 4 -- every row start and tile column is 16-byte aligned: 16-byte
+// loads, 8-byte stores.  !AL (e.g. the 181 x 217 x 181 example volume): the same kernel with
+// element-wise predicated 4-byte loads and stores.
+template <int HW, bool AL>
 __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
 {
     constexpr int W = 2 * HW + 1;
@@ -170,15 +173,23 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
         const int frp = tid / AWQ, fq = tid - frp * AWQ;
         const int fy = y0 - HW + 2 * frp;
         const int fx = x0 - HWA + 4 * fq;
-        const bool fill_thread = tid < NRP * AWQ && fx >= 0 && fx + 3 <= nx - 1;
+        const bool fill_thread = tid < NRP * AWQ && (AL ? (fx >= 0 && fx + 3 <= nx - 1) : (fx + 3 >= 0 && fx <= nx - 1));
         const bool row0_ok = fill_thread && fy >= 0 && fy < ny;
         const bool row1_ok = fill_thread && fy + 1 >= 0 && fy + 1 < ny;
-        const float *g0 = P.src + (size_t)(row0_ok ? fy : 0) * nx + (fill_thread ? fx : 0);
-        const float *g1 = P.src + (size_t)(row1_ok ? fy + 1 : 0) * nx + (fill_thread ? fx : 0);
+        const float *g0 = P.src + (ptrdiff_t)((size_t)(row0_ok ? fy : 0) * nx) + (fill_thread ? fx : 0);
+        const float *g1 = P.src + (ptrdiff_t)((size_t)(row1_ok ? fy + 1 : 0) * nx) + (fill_thread ? fx : 0);
         const int fdst_off = frp * APITCH + 4 * fq;
         const bool fswap = (lane & 4) != 0;
         auto load4 = [&](const float *row, bool ok) -> float4 {
-            return ok ? __ldg(reinterpret_cast<const float4 *>(row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (AL) return ok ? __ldg(reinterpret_cast<const float4 *>(row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {  // columns outside [0, nx-1] stay zero; the mirror patch fills the ones that are read
+                if (fx >= 0 && fx <= nx - 1) r.x = __ldg(row);
+                if (fx + 1 >= 0 && fx + 1 <= nx - 1) r.y = __ldg(row + 1);
+                if (fx + 2 >= 0 && fx + 2 <= nx - 1) r.z = __ldg(row + 2);
+                if (fx + 3 >= 0 && fx + 3 <= nx - 1) r.w = __ldg(row + 3);
+            }
+            return r;
         };
         auto store_item = [&](float2 *Adst, const float4 a, const float4 b) {
             if (!fill_thread) return;
@@ -366,8 +377,16 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
                     acc[r][0] = add2(prod[0], K.pz, K);
                 }
                 if (zout < sg.zb && zout >= sg.za) {
-                    *reinterpret_cast<u64 *>(optr) = acc[0][W - 1];
-                    *reinterpret_cast<u64 *>(optr + nx) = acc[1][W - 1];
+                    if (AL) {
+                        *reinterpret_cast<u64 *>(optr) = acc[0][W - 1];
+                        *reinterpret_cast<u64 *>(optr + nx) = acc[1][W - 1];
+                    } else {
+                        float a0, a1, b0, b1;
+                        upk(acc[0][W - 1], a0, a1);
+                        upk(acc[1][W - 1], b0, b1);
+                        optr[0] = a0, optr[1] = a1;
+                        optr[nx] = b0, optr[nx + 1] = b1;
+                    }
                 }
             }
             if (PF2) {
@@ -413,18 +432,24 @@ void mirror_table(int n, MirrorTab &m)
     }
 }
 
-template <int HW>
-int launch(s3d_engine *e, const FusedParams &P, int grid, size_t smem)
+template <int HW, bool AL>
+int launch_al(s3d_engine *e, const FusedParams &P, int grid, size_t smem)
 {
     static bool attr_set[64] = {};
     if (!attr_set[e->device & 63]) {
-        S3D_CUDA(e, cudaFuncSetAttribute(k_blur_fused<HW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        S3D_CUDA(e, cudaFuncSetAttribute(k_blur_fused<HW, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024));
         attr_set[e->device & 63] = true;
     }
-    k_blur_fused<HW><<<grid, NT, smem, e->stream>>>(P);
+    k_blur_fused<HW, AL><<<grid, NT, smem, e->stream>>>(P);
     S3D_LAUNCH_CHECK(e);
     return 0;
+}
+
+template <int HW>
+int launch(s3d_engine *e, const FusedParams &P, int grid, size_t smem)
+{
+    return (P.nx & 3) ? launch_al<HW, false>(e, P, grid, smem) : launch_al<HW, true>(e, P, grid, smem);
 }
 
 }  // namespace
@@ -435,7 +460,7 @@ bool s3d_blur_fused_eligible(int nx, int ny, int nz, int nc, const TapSet &taps,
     if (nc != 1 || hw < 1 || hw > MAXHW) return false;
     if (uf[0] != 1.0f || uf[1] != 1.0f || uf[2] != 1.0f) return false;
     if (nx < TX || ny < TY || nz < 2 * hw + 2 || nx < 2 * hw + 2 || ny < 2 * hw + 2) return false;
-    if ((nx & 3) || nz + 2 * hw + 4 > 32000) return false;  // 16-byte loads; short task table
+    if (nz + 2 * hw + 4 > 32000) return false;  // short task table
     for (int i = 0; i < taps.width; i++)
         if (taps.t[i] != taps.t[taps.width - 1 - i]) return false;  // Z phase shares products
     if (smem_bytes(hw, nz) > 200 * 1024) return false;
