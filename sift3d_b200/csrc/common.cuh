@@ -76,8 +76,10 @@ struct s3d_engine {
     int blur_mode = 0;
     int opt_icos_fast = 1;
     int opt_desc_v1 = 0;
+    int opt_desc_pre = 0;  // 1: k_descriptor3 fetches the next voxel's gradient one trip ahead
     int opt_desc_v2 = 0;  // 1: k_descriptor2 (raster-order rows) instead of k_descriptor3 (cell-owner lanes)
     int opt_orient_scalar = 0;  // 1: k_orient_group reads the level (7 loads) instead of the gradient volume
+    int opt_orient_g = 8;       // lanes per candidate of k_orient_group (8, 16 or 32)
     int opt_orient_v1 = 0;  // 1: thread-per-candidate k_orient instead of k_orient_group (A/B, tests)
     int ori_max_twx = 0;       // widest weight-table row of the current orientation tables
     int opt_orient_batch = 4;  // voxels k_orient fetches ahead (4, or 8 = line-aligned batches)

@@ -237,6 +237,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "blur_mode")) e->blur_mode = value;
     else if (!strcmp(name, "desc_v1")) e->opt_desc_v1 = value;
     else if (!strcmp(name, "desc_v2")) e->opt_desc_v2 = value;
+    else if (!strcmp(name, "desc_pre")) e->opt_desc_pre = value;
     else if (!strcmp(name, "slab_timing")) e->opt_slab_timing = value;
     else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 7;
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
@@ -246,6 +247,7 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "orient_batch")) e->opt_orient_batch = value;
     else if (!strcmp(name, "orient_v1")) e->opt_orient_v1 = value;
     else if (!strcmp(name, "orient_scalar")) e->opt_orient_scalar = value;
+    else if (!strcmp(name, "orient_g")) e->opt_orient_g = value;
     else if (!strcmp(name, "blur_dbg")) {
         DeviceGuard guard(e->device);
         if (value && !e->d_blur_dbg) {

@@ -686,11 +686,10 @@ __global__ void __launch_bounds__(128, TAB ? (BATCH == 8 ? 6 : 8) : 4)
 //   * The f64 structure tensor is order-insensitive at the 1e-16 level (its eigenvectors are
 //     rounded to f32, and no decision sits within 1e-15 of its threshold): per-lane partial
 //     sums, combined with a 3-step butterfly.
-#define ORI_G 8
 #define ORI_WARPS 4
 // SCALAR: central differences from the level itself (7 x 4-byte loads, 4 bytes of footprint per
 // voxel) instead of the float4 gradient volume (one 16-byte load, 16 bytes of footprint)
-template <bool SCALAR>
+template <int ORI_G, bool SCALAR>
 __global__ void __launch_bounds__(32 * ORI_WARPS)
     k_orient_group(s3d_keypoint *__restrict__ kps, int n, PyrTable T, double sig_fctr,
                    double corner_thresh, unsigned char *__restrict__ ok,
@@ -771,16 +770,14 @@ __global__ void __launch_bounds__(32 * ORI_WARPS)
             st[2 * ORI_G + gl] = tz;
             __syncwarp();
             if (gl < 3) {  // the reference's order: voxel after voxel (sift.c:1416-1417)
-                const float4 v0 = *reinterpret_cast<const float4 *>(st + ORI_G * gl);
-                const float4 v1 = *reinterpret_cast<const float4 *>(st + ORI_G * gl + 4);
-                wsum = fa(wsum, v0.x);
-                wsum = fa(wsum, v0.y);
-                wsum = fa(wsum, v0.z);
-                wsum = fa(wsum, v0.w);
-                wsum = fa(wsum, v1.x);
-                wsum = fa(wsum, v1.y);
-                wsum = fa(wsum, v1.z);
-                wsum = fa(wsum, v1.w);
+#pragma unroll
+                for (int q = 0; q < ORI_G / 4; q++) {
+                    const float4 v = *reinterpret_cast<const float4 *>(st + ORI_G * gl + 4 * q);
+                    wsum = fa(wsum, v.x);
+                    wsum = fa(wsum, v.y);
+                    wsum = fa(wsum, v.z);
+                    wsum = fa(wsum, v.w);
+                }
             }
             __syncwarp();
         }
@@ -1722,7 +1719,7 @@ __device__ __forceinline__ u64x mul2x(u64x a, u64x b)
 #define D3_MAGIC 12582912.0f
 #define D3_MAGIC_BITS 0x4B400000u
 
-template <int OCC, bool FAST>
+template <int OCC, bool FAST, bool PRE>
 __global__ void __launch_bounds__(D3_THREADS, OCC)
     k_descriptor3(const s3d_keypoint *__restrict__ kps, int n, PyrTable T,
                   const MeshDev *__restrict__ M, unsigned char *__restrict__ out)
@@ -1857,6 +1854,8 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
     unsigned yz = 0;      // y | z << 16 of the current row
     unsigned vidx = 0;    // voxel index of the current voxel in the level
     const float mag_scale = fx_scale;
+    float4 gpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool pre_ok = false;
 
     for (;;) {
         const bool starving = rem == 0 && nq == 0 && !scan_done;
@@ -1895,6 +1894,7 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
             yz = rec.y;
             xf = (float)xa;
             vidx = xa + (unsigned)nx * ((yz & 0xffffu) + (unsigned)ny * (yz >> 16));
+            pre_ok = false;
         }
         // ---- one voxel (sift.c:1866-1905) --------------------------------------------------
         float sq, dv[3];
@@ -1904,8 +1904,17 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         xf = fa(xf, 1.0f);
         vidx++;
         rem--;
+        // the next voxel of the row is fetched one trip ahead (PRE): the gather is the longest
+        // latency of the loop and the lanes sit in 32 different lines
+        float4 g4;
+        if (PRE) {
+            g4 = pre_ok ? gpre : __ldg(gim + vi);
+            pre_ok = rem > 0;
+            if (pre_ok) gpre = __ldg(gim + vidx);
+        } else {
+            g4 = __ldg(gim + vi);
+        }
         if (!member) continue;
-        const float4 g4 = __ldg(gim + vi);
         float g[3] = {g4.x, g4.y, g4.z};
         // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument, glibc's expf
         const float wgt_win = expf_glibc_t(__fdiv_rn(fm(-0.5f, sq), ld_shared_f32(kc_addr + 4u)), etab);
@@ -2502,16 +2511,21 @@ int s3d_k_orientations(s3d_engine *e, double corner_thresh)
                 if (sidx >= 0 && sidx < e->K && !e->grad[lv]) grads = false;
             }
             if (e->ori_lists_ok && !e->opt_orient_v1) {  // grouped kernel
-                const int per_cta = ORI_WARPS * (32 / ORI_G);
+                const int G = e->opt_orient_g == 16 || e->opt_orient_g == 32 ? e->opt_orient_g : 8;
+                const int per_cta = ORI_WARPS * (32 / G);
                 const int grid = (n + per_cta - 1) / per_cta;
-                if (grads && !e->opt_orient_scalar)
-                    k_orient_group<false><<<grid, 32 * ORI_WARPS, 0, e->stream>>>(
-                        e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok,
-                        static_cast<const OriTab *>(e->d_ori_tabs), static_cast<const int2 *>(e->d_ori_lists));
-                else
-                    k_orient_group<true><<<grid, 32 * ORI_WARPS, 0, e->stream>>>(
-                        e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok,
-                        static_cast<const OriTab *>(e->d_ori_tabs), static_cast<const int2 *>(e->d_ori_lists));
+                const bool sc = !grads || e->opt_orient_scalar;
+                const OriTab *tb = static_cast<const OriTab *>(e->d_ori_tabs);
+                const int2 *ls = static_cast<const int2 *>(e->d_ori_lists);
+#define S3D_ORI_LAUNCH(GG, SC) \
+    k_orient_group<GG, SC><<<grid, 32 * ORI_WARPS, 0, e->stream>>>(e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, tb, ls)
+                if (G == 8 && !sc) S3D_ORI_LAUNCH(8, false);
+                else if (G == 8) S3D_ORI_LAUNCH(8, true);
+                else if (G == 16 && !sc) S3D_ORI_LAUNCH(16, false);
+                else if (G == 16) S3D_ORI_LAUNCH(16, true);
+                else if (!sc) S3D_ORI_LAUNCH(32, false);
+                else S3D_ORI_LAUNCH(32, true);
+#undef S3D_ORI_LAUNCH
             } else if (e->opt_orient_batch == 8)
                 k_orient<true, 8><<<(n + 127) / 128, 128, 0, e->stream>>>(
                     e->d_kp_all, n, T, 1.5, corner_thresh, e->d_ok, nullptr,
@@ -2551,11 +2565,13 @@ int s3d_k_descriptors(s3d_engine *e, const s3d_keypoint *d_kp, int n, unsigned c
     }
     if (v3) {
         if (!(e->opt_icos_fast & 1))
-            k_descriptor3<4, false><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+            k_descriptor3<4, false, false><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
         else if (e->opt_desc_occ == 3)
-            k_descriptor3<3, true><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+            k_descriptor3<3, true, true><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+        else if (e->opt_desc_pre)
+            k_descriptor3<4, true, true><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
         else
-            k_descriptor3<4, true><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
+            k_descriptor3<4, true, false><<<n, D3_THREADS, 0, e->stream>>>(d_kp, n, T, e->d_mesh, d_out);
         S3D_LAUNCH_CHECK(e);
         return 0;
     }

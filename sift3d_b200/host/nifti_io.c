@@ -121,7 +121,7 @@ int read_nii(const char *path, Image *const im)
     int dims[4] = {1, 1, 1, 1};
 
     if ((f = gzopen(path, "rb")) == NULL) { /* gzopen also reads plain .nii */
-        NII_ERR("read_nii: failure loading file %s", path);
+        NII_ERR("read_nii: failure loading file %s\n", path);
         return SIFT3D_FAILURE;
     }
     if (gz_read_all(f, &h, sizeof(h))) goto fail_msg;
@@ -166,6 +166,21 @@ int read_nii(const char *path, Image *const im)
     im->zs = im->ys * (size_t)im->ny;
     nvox = (size_t)im->nx * im->ny * im->nz;
     size = nvox * (size_t)im->nc;
+    /* untrusted header: the voxel count must fit the reference's own `int` size arithmetic
+     * (im_resize, imutil.c:1533) and vox_offset must be a finite value in [352, 2^31) */
+    if ((double)im->nx * im->ny * im->nz * im->nc > 2147483647.0) {
+        NII_ERR("read_nii: image in %s is too large (%d x %d x %d x %d)\n", path, im->nx, im->ny,
+                im->nz, im->nc);
+        gzclose(f);
+        return SIFT3D_FAILURE;
+    }
+    if (!isfinite(h.vox_offset) || h.vox_offset < 352.0f || h.vox_offset > 2147483647.0f) {
+        if (!(h.vox_offset == 0.0f)) { /* 0: some writers leave it unset for .nii; data follow at 352 */
+            NII_ERR("read_nii: invalid vox_offset %g in %s\n", (double)h.vox_offset, path);
+            gzclose(f);
+            return SIFT3D_FAILURE;
+        }
+    }
     if (im->size != size || im->data == NULL) { /* im_resize, imutil.c:1523 */
         float *p = (float *)realloc(im->data, size * sizeof(float));
         if (p == NULL) goto fail_msg;
@@ -173,7 +188,7 @@ int read_nii(const char *path, Image *const im)
         im->size = size;
     }
     /* voxel data start at vox_offset (>= 352); extensions in between are skipped */
-    skip = h.vox_offset > 348.0f ? (size_t)h.vox_offset - 348 : 4;
+    skip = h.vox_offset >= 352.0f ? (size_t)h.vox_offset - 348 : 4;
     {
         unsigned char junk[4096];
         while (skip) {
@@ -221,7 +236,7 @@ int read_nii(const char *path, Image *const im)
     return SIFT3D_SUCCESS;
 
 fail_msg:
-    NII_ERR("read_nii: failure loading file %s", path);
+    NII_ERR("read_nii: failure loading file %s\n", path);
     if (f) gzclose(f);
     free(raw);
     return SIFT3D_FAILURE;

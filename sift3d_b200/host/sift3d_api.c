@@ -1407,11 +1407,35 @@ int sift3d_b200_im_inv_transform_affine(const double A[12], const Image *const s
                             src->data[c + x * src->xs + y * src->ys + z * src->zs];
         data = tmp;
     }
-    image_default_stride(dst);
-    pthread_mutex_lock(&g_util_lock);
-    rc = s3d_resample_affine(e, data, src->nx, src->ny, src->nz, src->nc, A, interp, dst->data,
-                             dst->nx, dst->ny, dst->nz);
-    pthread_mutex_unlock(&g_util_lock);
+    {   /* the reference writes through SIFT3D_IM_GET_VOX, i.e. the caller's dst strides
+         * (imutil.c:2062-2076): resample into a contiguous buffer and scatter when they are not
+         * the default ones; dst->xs/ys/zs are never modified */
+        const int dst_default = dst->xs == (size_t)dst->nc && dst->ys == (size_t)dst->nc * dst->nx &&
+                                dst->zs == (size_t)dst->nc * dst->nx * dst->ny;
+        float *out = dst->data, *otmp = NULL;
+        const size_t dn = (size_t)dst->nx * dst->ny * dst->nz * dst->nc;
+        if (!dst_default) {
+            if ((otmp = (float *)malloc(dn * sizeof(float))) == NULL) {
+                free(tmp);
+                return SIFT3D_FAILURE;
+            }
+            out = otmp;
+        }
+        pthread_mutex_lock(&g_util_lock);
+        rc = s3d_resample_affine(e, data, src->nx, src->ny, src->nz, src->nc, A, interp, out,
+                                 dst->nx, dst->ny, dst->nz);
+        pthread_mutex_unlock(&g_util_lock);
+        if (otmp && !rc) {
+            int x, y, z, c;
+            for (z = 0; z < dst->nz; z++)
+                for (y = 0; y < dst->ny; y++)
+                    for (x = 0; x < dst->nx; x++)
+                        for (c = 0; c < dst->nc; c++)
+                            dst->data[c + x * dst->xs + y * dst->ys + z * dst->zs] =
+                                otmp[c + (size_t)dst->nc * (x + (size_t)dst->nx * (y + (size_t)dst->ny * z))];
+        }
+        free(otmp);
+    }
     free(tmp);
     return rc ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
 }

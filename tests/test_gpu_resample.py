@@ -67,3 +67,27 @@ def test_linear_large_matches_property(b200_lib):
     want = np.zeros_like(vol)
     want[:96 - 5, 2:, :160 - 3] = vol[5:, :128 - 2, 3:]
     assert np.array_equal(got, want)
+
+
+def test_inv_transform_honours_dst_strides(b200_lib, oracle_cls):
+    """im_inv_transform writes through SIFT3D_IM_GET_VOX (imutil.c:2062-2076): a caller-owned
+    dst with padded rows keeps its strides and gets the voxels where they say."""
+    import ctypes as C
+    from sift3d_b200 import capi
+    rng = np.random.default_rng(4)
+    vol = rng.random((12, 14, 16), dtype=np.float32)
+    A = np.array([[0.9, 0.1, 0.0, 0.5], [-0.1, 1.0, 0.05, 0.2], [0.0, 0.02, 1.1, -0.3]])
+    want = oracle_cls().resample_affine(vol, A, (10, 11, 13))
+    big = np.full((10, 11, 20), -7.0, np.float32)          # rows padded from 13 to 20 floats
+    src = capi.make_image(vol)
+    dst = capi.make_image(big)
+    dst.nx = 13
+    dst.size = 10 * 11 * 13
+    Aflat = np.ascontiguousarray(A, np.float64).reshape(12)
+    f = b200_lib.lib.sift3d_b200_im_inv_transform_affine
+    f.argtypes = [C.c_void_p, C.POINTER(capi.Image), C.c_int, C.c_int, C.POINTER(capi.Image)]
+    f.restype = C.c_int
+    assert f(Aflat.ctypes.data, C.byref(src), 0, 0, C.byref(dst)) == 0
+    assert (dst.xs, dst.ys, dst.zs) == (1, 20, 220)       # untouched
+    assert np.array_equal(big[:, :, :13].view(np.uint32), want.view(np.uint32))
+    assert (big[:, :, 13:] == -7.0).all()                 # the padding was not written

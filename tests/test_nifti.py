@@ -138,3 +138,33 @@ def test_reads_the_reference_example_volume(nii):
     assert got.shape == (181, 217, 181, 1) and units == wunits == (1.0, 1.0, 1.0)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert got.max() > 0
+
+
+def test_read_nii_rejects_hostile_headers(nii, tmp_path):
+    """The header comes from an untrusted file: a non-finite or out-of-range vox_offset and a
+    voxel count beyond the reference's own `int` size arithmetic (imutil.c:1533) are refused
+    instead of driving the skip loop / the allocation."""
+    from sift3d_b200 import capi
+    vol = np.arange(4 * 5 * 6, dtype=np.float32).reshape(4, 5, 6)
+    good = tmp_path / "good.nii"
+    im = capi.make_image(vol)
+    assert nii.write_nii(str(good).encode(), C.byref(im)) == 0
+    raw = bytearray(good.read_bytes())
+
+    def attempt(patch):
+        b = bytearray(raw)
+        patch(b)
+        p = tmp_path / "bad.nii"
+        p.write_bytes(bytes(b))
+        out = capi.empty_image()
+        rc = nii.read_nii(str(p).encode(), C.byref(out))
+        if rc == 0 and out.data:
+            C.CDLL(None).free(C.cast(out.data, C.c_void_p))
+        return rc
+
+    assert attempt(lambda b: None) == 0
+    assert attempt(lambda b: b.__setitem__(slice(108, 112), struct.pack("<f", float("inf")))) != 0
+    assert attempt(lambda b: b.__setitem__(slice(108, 112), struct.pack("<f", float("nan")))) != 0
+    assert attempt(lambda b: b.__setitem__(slice(108, 112), struct.pack("<f", 350.0))) != 0
+    assert attempt(lambda b: b.__setitem__(slice(108, 112), struct.pack("<f", 3e9))) != 0
+    assert attempt(lambda b: b.__setitem__(slice(42, 48), struct.pack("<3h", 32767, 32767, 32767))) != 0
