@@ -1658,6 +1658,7 @@ __global__ void __launch_bounds__(DESC2_THREADS, OCC)
 #define D3_THREADS 256
 #define D3_VSTRIDE 352
 #define D3_RING 8
+#define D3_WTAB 1312
 struct D3Smem {
     unsigned h[12 * D3_VSTRIDE];
     unsigned long long tab[32];
@@ -1665,6 +1666,8 @@ struct D3Smem {
     int lut[32];
     float kc[4];  // r2, s2
     D3Scan scan;  // row-scan constants of the keypoint
+    // window weights by squared integer distance (see the kernel): n = |offset|^2 in voxels
+    float wtab[D3_WTAB];
     int4 cur[D3_THREADS];  // per-lane scan cursor {next row, rows in the bounding box, BY, ylo | zlo << 16}
     uint2 ring[D3_THREADS / 32][D3_RING][32];  // per-lane queue of scanned rows {xa | cnt << 16, y | z << 16}
 };
@@ -1798,6 +1801,25 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
         if (lane == 0) s_gmax[warp] = m2;
     }
+    // Window weights from a table.  For an integer centre and isotropic power-of-two units u
+    // (every detector keypoint of a volume with such units) the offsets v are u * integers, so
+    // the squared distance the reference forms, (vx*vx + vy*vy) + vz*vz in f32, is EXACTLY
+    // u^2 * n with n = dx^2 + dy^2 + dz^2 < 2^24: the weight expf(-0.5f * sq / sigma^2)
+    // (sift.c:1890) depends on n alone.  Tabulated once per keypoint with the per-voxel
+    // arithmetic (bit-identical), it replaces an IEEE division and the f64 exp (33 of ~380
+    // instructions per voxel).  Other keypoints take the arithmetic path (block-uniform).
+    bool tab_ok;
+    float inv_u2 = 0.0f, nmaxf = 0.0f;
+    {
+        int ex;
+        const bool pow2 = frexpf(uxf, &ex) == 0.5f;
+        const bool iso = uxf == uyf && uyf == uzf;
+        const bool integer = kp.x == floorf(kp.x) && kp.y == floorf(kp.y) && kp.z == floorf(kp.z);
+        inv_u2 = iux * iux;
+        nmaxf = K.r2 * inv_u2;
+        tab_ok = pow2 && iso && integer && nmaxf < (float)(D3_WTAB - 1);
+    }
+    const unsigned wtab_addr = sb + (unsigned)offsetof(D3Smem, wtab);
     // ---- this lane's cell and its rows ---------------------------------------------------
     const int ib0 = lane & 3, ib1 = (lane >> 2) & 3, ib2 = 2 * (warp & 1) + (lane >> 4);
     bool scan_done;
@@ -1811,6 +1833,12 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         scan_done = (warp >> 1) >= nrows;
     }
     __syncthreads();
+    if (tab_ok) {  // the exp table (S.tab) is visible now; the second barrier publishes wtab
+        const int nmax = (int)nmaxf;
+        const float u2 = uxf * uxf;
+        for (int nn = tid; nn <= nmax; nn += D3_THREADS)
+            S.wtab[nn] = expf_glibc_t(__fdiv_rn(fm(-0.5f, fm((float)nn, u2)), s2), etab);
+    }
 #pragma unroll
     for (int i = 0; i < D3_THREADS / 32; i++) m2 = fmaxf(m2, s_gmax[i]);
     // Fixed-point scale 2^S (block-uniform).  A contribution is mag * 2^S * w_c * bary with
@@ -1917,7 +1945,11 @@ __global__ void __launch_bounds__(D3_THREADS, OCC)
         if (!member) continue;
         float g[3] = {g4.x, g4.y, g4.z};
         // sift.c:1890: expf(-0.5f * sq_dist / (sigma * sigma)), f32 argument, glibc's expf
-        const float wgt_win = expf_glibc_t(__fdiv_rn(fm(-0.5f, sq), ld_shared_f32(kc_addr + 4u)), etab);
+        float wgt_win;
+        if (tab_ok)
+            wgt_win = ld_shared_f32(wtab_addr + 4u * (unsigned)__float2int_rn(fm(sq, inv_u2)));
+        else
+            wgt_win = expf_glibc_t(__fdiv_rn(fm(-0.5f, sq), ld_shared_f32(kc_addr + 4u)), etab);
         g[0] = fm(g[0], wgt_win);
         g[1] = fm(g[1], wgt_win);
         g[2] = fm(g[2], wgt_win);
