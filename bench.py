@@ -297,6 +297,32 @@ def run_reference_arm(args):
     }))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: keep this rank's threads (and so its first-touch host memory: the
+    volume, the pinned staging ring) on the NUMA node its GPU hangs off -- what `numactl` would
+    do in a deployment.  Best effort: returns a description, or None when the topology is not
+    readable (then nothing is changed)."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        bdf = f"{torch.cuda.get_device_properties(local_rank).pci_domain_id:04x}:{bdf:02x}:" \
+              f"{torch.cuda.get_device_properties(local_rank).pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------- device plumbing
 def bind_cuda(capi):
     cu = C.CDLL(str(capi.CUDA_LIB))
@@ -493,6 +519,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
     ap.add_argument("--no-slab", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not bind each rank to the NUMA node of its GPU")
     ap.add_argument("--dense-size", type=int, default=256)
     ap.add_argument("--slab-nx", type=int, default=2048)
     ap.add_argument("--slab-ny", type=int, default=2048)
@@ -528,6 +556,7 @@ def main():
         dist = dist_mod
         sdist.init_process_group("nccl", device=dev)
     os.environ["SIFT3D_CUDA_DEVICE"] = str(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
 
     n = args.size
     nvox = n ** 3
@@ -733,7 +762,8 @@ def main():
                                    f"blob_volume({n}, seed {SEED} + rank)",
                        "candidates": ncand, "keypoints": nkp, "golden_check": golden_note,
                        "l2_note": f"inputs ({4 * nvox >> 20} MiB/level) larger than the 126 MB L2",
-                       "parallelism": f"independent volumes x{world}, no data-path collective"},
+                       "parallelism": f"independent volumes x{world}, no data-path collective" +
+                                      (f"; ranks bound to their GPU's NUMA node (rank 0: {numa})" if numa else "")},
             "e2e": {"value": nvox * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 4 * nvox, "d2h_bytes_per_step": int(d2h),
                     "source": "pageable (malloc) host volume, as a stock im_read caller has",
