@@ -32,6 +32,8 @@
 // phase share products: (hw+1) multiplies + (2hw+1) adds per voxel pair.
 #include "common.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -407,6 +409,443 @@ __global__ void __launch_bounds__(NT, 1) k_blur_fused(const FusedParams P)
     }
 }
 
+// =====================================================================================================
+// k_blur_tma -- the same fused blur, second design (round 2).  What changed, and why (ncu on
+// k_blur_fused: 56 warp-instructions per 32 voxels at w = 5 of which 15 are FFMA2; the rest is the
+// fill path, transposition MOVs, the rotation of the Z partial sums and per-step bookkeeping
+// amortised over only 4 voxels per thread):
+//   fill   TMA (cp.async.bulk.tensor.3d, out-of-bounds elements zero-filled) + one mbarrier per ring
+//          slot, issued by one thread NSA+1 planes ahead: no LDG / STS / address arithmetic in the
+//          compute warps, and the tile lies in shared memory as it lies in global memory (TMA cannot
+//          interleave two rows, which is what k_blur_fused's row-pair FFMA2 operands need).
+//   X      item = R consecutive outputs of ONE row (R = 8, or 16 with the tall tile).  The packed
+//          operand is the TAP pair (t[a], t[a+1]) and the sample is the broadcast scalar:
+//          (o[x], o[x+1]) += (t[a], t[a+1]) * in[s] with a = x - s + hw.  Every sample is used as a
+//          scalar, so no operand needs a particular register-pair alignment (a sliding window of
+//          x-PAIRS would need each pair at both alignments); the tap pairs at both alignments are two
+//          small tables.  Each output still receives its taps in the reference's order (samples
+//          descending); the table is padded with t[-1] = t[w] = +0, which adds an exact zero before
+//          the first / after the last tap of one lane -- a no-op, because a partial sum that started
+//          from +0 is never -0.  (Only non-finite input differs: 0 * Inf = NaN where the reference
+//          has Inf.)  X results are x-pairs: no transposition before the Y phase.
+//   Y, Z   a thread owns RPT rows x one x-pair (RPT = 4 for the narrow filters: a 64 x 64 tile,
+//          8 voxels per thread and step; RPT = 2 where the 2 x RPT x w partial sums would not fit)
+//   loop   unrolled three times: the rotation of the partial sums costs register moves only at
+//          the back edge (every third plane)
+// Arithmetic and boundary rules are those of k_blur_fused (bit-identical output; the parity tests
+// run both against the oracle).  TMA constraints found on B200 (tools/tma_probe.cu): the box must
+// fit into the tensor in every dimension and its x origin must be 16-byte aligned -- so the x
+// halo is rounded up to a multiple of 4 columns and small volumes stay with k_blur_fused.
+// =====================================================================================================
+constexpr int BP2 = 66;  // floats per row of B: 8-byte aligned rows, lanes walking down the rows hit different banks (STS.64)
+
+__host__ __device__ constexpr int tma_hwa(int hw) { return (hw + 3) & ~3; }
+__host__ __device__ constexpr int tma_aw(int hw)
+{  // box width: TX + 2 x halo, with an ODD number of 16-byte chunks per row, so that lanes walking
+   // down the rows hit different banks (LDS.128)
+    int aw = TX + 2 * tma_hwa(hw);
+    if (((aw / 4) & 1) == 0) aw += 4;
+    return aw;
+}
+__host__ __device__ constexpr int tma_slot_bytes(int hw, int rpt)
+{
+    return (((16 * rpt + 2 * hw) * tma_aw(hw) * 4) + 127) & ~127;
+}
+__host__ __device__ constexpr int tma_b_bytes(int hw, int rpt) { return 3 * (16 * rpt + 2 * hw) * BP2 * 4; }
+constexpr int TMA_NSA = 4;  // A-ring slots
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int x, int y, int z, unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+struct TapPairs {  // (t[a], t[a+1]) for even a (e[a/2]) and odd a (o[(a+1)/2]), t[-1] = t[w] = +0
+    float2 e[MAXHW + 1], o[MAXHW + 1];
+};
+
+template <int HW, int RPT>
+__global__ void __launch_bounds__(NT, 1)
+    k_blur_tma(const __grid_constant__ CUtensorMap tmap, const FusedParams P, const TapPairs TP)
+{
+    constexpr int W = 2 * HW + 1;
+    constexpr int HWA = tma_hwa(HW);     // x halo fetched (column 0 of A is x0 - HWA)
+    constexpr int OFF = HWA - HW;        // first column of run 0's window
+    constexpr int TYT = 16 * RPT;        // tile rows
+    constexpr int NR = TYT + 2 * HW;     // rows of the A / B tiles
+    constexpr int AW = tma_aw(HW);       // columns of A
+    constexpr int R = RPT == 4 ? 16 : 8;  // outputs of an X item
+    constexpr int L = R + 2 * HW;        // its window
+    constexpr int NQ = (OFF + L + 3) / 4;  // 16-byte loads covering it
+    constexpr int NXI = NR * (TX / R);   // X items of a plane
+    constexpr int NSA = TMA_NSA, PDA = NSA + 1;
+    constexpr int SLOTB = tma_slot_bytes(HW, RPT);
+    constexpr unsigned TXB = (unsigned)NR * AW * 4u;  // bytes one plane's box delivers
+    static_assert(NXI <= NT, "one X item per thread");
+    extern __shared__ unsigned char smem_dyn[];
+    // 128-byte aligned window (TMA destinations)
+    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    float *Abuf = reinterpret_cast<float *>(smem_raw);                    // NSA x [NR][AW]
+    float *Bbuf = reinterpret_cast<float *>(smem_raw + NSA * SLOTB);       // 3 x [NR][BP2]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(Bbuf + 3 * NR * BP2);
+    short *task_plane = reinterpret_cast<short *>(bars + NSA);
+    unsigned char *task_mode = reinterpret_cast<unsigned char *>(task_plane + (P.nz + 2 * HW + 4));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nx = P.nx, ny = P.ny, nz = P.nz;
+    const size_t plane_stride = (size_t)nx * ny;
+    Consts K;
+    K.nz = pk(P.c_negzero, P.c_negzero);
+    K.one = pk(P.c_one, P.c_one);
+    K.pz = pk(P.c_zero, P.c_zero);
+    const unsigned bar0 = smem_u32(bars), a0s = smem_u32(Abuf);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NSA; i++) mbar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    unsigned segbase = 0;  // planes fetched by this CTA so far: plane G sits in slot G % NSA, phase G / NSA
+
+    // X item of this thread: row xrow of the tile (lanes = consecutive rows), outputs R*xrun .. +R-1
+    const bool x_thread = tid < NXI;
+    const int xrun = tid / NR, xrow = tid - xrun * NR;
+    const bool producer = tid == NT - 32;  // lane 0 of the last warp (never an X warp)
+
+    for (int si = P.seg_start[blockIdx.x]; si < P.seg_start[blockIdx.x + 1]; si++) {
+        const Seg sg = P.segs[si];
+        const int x0 = sg.x0, y0 = sg.y0;
+        // ---- task list: samples j = zb-1+HW .. za-HW of the extended z line (as in k_blur_fused) ----
+        __syncthreads();
+        int ntask, tmain;
+        {
+            const int dim_end = nz - 1;
+            const int jt = sg.zb - 1 + HW, jb = sg.za - HW;
+            const int nlerp = jt >= dim_end ? jt - dim_end + 1 : 0;
+            ntask = (jt - jb + 1) + (nlerp ? 1 : 0);
+            tmain = nlerp ? nlerp + 1 : 0;  // the stashed plane and the lerped samples come first
+            for (int t = tid; t < ntask; t += NT) {
+                int plane, mode;
+                if (nlerp && t == 0) {
+                    plane = P.mz.lo[jt - dim_end];
+                    mode = MODE_STASH;
+                } else {
+                    const int j = jt - (t - (nlerp ? 1 : 0));
+                    if (j >= dim_end) {
+                        plane = P.mz.lo[j - dim_end] + 1;
+                        mode = MODE_LERP | ((j - dim_end) << 2);
+                    } else {
+                        plane = j < 0 ? -j : j;
+                        mode = MODE_NORMAL;
+                    }
+                }
+                task_plane[t] = (short)plane;
+                task_mode[t] = (unsigned char)mode;
+            }
+        }
+        const bool xedge = (x0 - HW < 0) || (x0 + TX + HW > nx - 1);
+        const bool yedge = (y0 - HW < 0) || (y0 + TYT + HW > ny - 1);
+        const int xo = x0 - HWA;  // global x of column 0 of A (a multiple of 4: 16-byte aligned origin)
+
+        // ---- producer: plane p of the task list -> ring slot, one box, one mbarrier phase ---------
+        auto produce = [&](int p) {
+            if (p < 0 || p >= ntask) return;
+            const unsigned G = segbase + (unsigned)p, slot = G % NSA;
+            const unsigned bar = bar0 + 8 * slot;
+            const int z = task_plane[p];
+            // the slot's previous contents were read (and, in edge tiles, patched) through the generic
+            // proxy before the barrier this thread has just passed
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, TXB);
+            tma_load_3d(a0s + slot * SLOTB, &tmap, xo, y0 - HW, z, bar);
+        };
+        auto wait_plane = [&](int p) {
+            const unsigned G = segbase + (unsigned)p;
+            mbar_wait(bar0 + 8 * (G % NSA), (G / NSA) & 1u);
+        };
+        auto a_slot = [&](int p) -> float * {
+            const unsigned G = segbase + (unsigned)p;
+            return Abuf + (size_t)(G % NSA) * (SLOTB / 4);
+        };
+
+        // ---- X phase: R outputs of one row per thread, samples streamed right to left.  Window
+        //      column c (sample s = R*xrun - HW + c) meets output pair q with the tap pair
+        //      (t[a], t[a+1]), a = 2q + 2HW - c in [-1, W-1]. -------------------------------------------
+        auto xphase = [&](const float *Ap, float *Bdst) {
+            if (!x_thread) return;
+            const float *er = Ap + xrow * AW + R * xrun;
+            float e[4 * NQ];
+#pragma unroll
+            for (int i = NQ - 1; i >= 0; i--) {
+                const float4 v = *reinterpret_cast<const float4 *>(er + 4 * i);
+                e[4 * i] = v.x, e[4 * i + 1] = v.y, e[4 * i + 2] = v.z, e[4 * i + 3] = v.w;
+            }
+            u64 o[R / 2];
+#pragma unroll
+            for (int q = 0; q < R / 2; q++) o[q] = K.pz;
+#pragma unroll
+            for (int c = L - 1; c >= 0; c--) {
+                const u64 v = pk(e[OFF + c], e[OFF + c]);
+#pragma unroll
+                for (int q = 0; q < R / 2; q++) {
+                    const int a = 2 * q + 2 * HW - c;
+                    if (a >= -1 && a <= W - 1) {
+                        const int ai = a < -1 || a > W - 1 ? 0 : a;
+                        const float2 tp = (ai & 1) ? TP.o[(ai + 1) / 2] : TP.e[ai / 2];
+                        o[q] = add2(mul2(pk(tp.x, tp.y), v, K), o[q], K);
+                    }
+                }
+            }
+            // 8-byte stores: ptxas does not place two FFMA2 results in one aligned register quad (a
+            // 16-byte store costs four moves); with BP2 = 2 (mod 4) they are conflict-free
+            u64 *brow = reinterpret_cast<u64 *>(Bdst + xrow * BP2 + R * xrun);
+#pragma unroll
+            for (int q = 0; q < R / 2; q++) brow[q] = o[q];
+        };
+
+        // ---- Y phase: rows RPT*warp .. +RPT-1 of the tile, x pair = lane; B rows streamed top-down
+        auto yphase = [&](const float *Bsrc, u64 *yacc) {
+#pragma unroll
+            for (int j = 0; j < RPT; j++) yacc[j] = K.pz;
+            const float *top = Bsrc + 2 * lane + (RPT * warp + RPT - 1 + 2 * HW) * BP2;
+#pragma unroll
+            for (int k = 0; k < W + RPT - 1; k++) {
+                const u64 v = *reinterpret_cast<const u64 *>(top - k * BP2);
+#pragma unroll
+                for (int j = RPT - 1; j >= 0; j--) {
+                    const int a = k - (RPT - 1 - j);
+                    if (a >= 0 && a < W) yacc[j] = add2(mul2(v, pk(P.taps.t[a < 0 || a >= W ? 0 : a], P.taps.t[a < 0 || a >= W ? 0 : a]), K), yacc[j], K);
+                }
+            }
+        };
+
+        // ---- mirror patches (edge tiles only; each runs a step before its consumer) ---------------
+        auto xpatch = [&](float *Ep) {  // columns outside [0, nx-1)
+            const int nl = x0 - HW < 0 ? HW - x0 : 0;  // x = x0-HW .. -1
+            const int nrt = x0 + TX + HW > nx - 1 ? x0 + TX + HW - (nx - 1) : 0;  // x = nx-1 ..
+            const int ncol = nl + nrt;
+            for (int e = tid; e < NR * ncol; e += NT) {
+                const int r = e / ncol, c = e - r * ncol;
+                float v;
+                int dc;
+                if (c < nl) {
+                    const int x = x0 - HW + c;  // < 0: copy of column -x
+                    dc = x - xo;
+                    v = Ep[r * AW + (-x - xo)];
+                } else {
+                    const int k = c - nl;  // x = nx-1+k: omf*col[lo] + f*col[lo+1]
+                    const int lo = P.mx.lo[k] - xo;
+                    v = __fadd_rn(__fmul_rn(P.mx.omf[k], Ep[r * AW + lo]), __fmul_rn(P.mx.f[k], Ep[r * AW + lo + 1]));
+                    dc = nx - 1 + k - xo;  // k = 0 overwrites its own `hi` (no other entry reads it)
+                }
+                Ep[r * AW + dc] = v;
+            }
+        };
+        auto ypatch = [&](float *Bp) {  // rows of B outside [0, ny-1)
+            const int nt_ = y0 - HW < 0 ? HW - y0 : 0;
+            const int nb_ = y0 + TYT + HW > ny - 1 ? y0 + TYT + HW - (ny - 1) : 0;
+            for (int e = tid; e < (nt_ + nb_) * TX; e += NT) {
+                const int rr = e / TX, x = e - rr * TX;
+                if (rr < nt_) {
+                    const int y = y0 - HW + rr;  // < 0: copy of row -y
+                    Bp[rr * BP2 + x] = Bp[(rr - 2 * y) * BP2 + x];
+                } else {
+                    const int k = rr - nt_;  // y = ny-1+k
+                    const int rl = P.my.lo[k] - (y0 - HW);
+                    const float v = __fadd_rn(__fmul_rn(P.my.omf[k], Bp[rl * BP2 + x]),
+                                              __fmul_rn(P.my.f[k], Bp[(rl + 1) * BP2 + x]));
+                    Bp[(ny - 1 + k - (y0 - HW)) * BP2 + x] = v;
+                }
+            }
+        };
+
+        u64 acc[RPT][W];  // Z-phase partial sums by age
+        u64 prevY[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; j++) {
+#pragma unroll
+            for (int a = 0; a < W; a++) acc[j][a] = K.pz;
+            prevY[j] = K.pz;
+        }
+        float *op[RPT];  // output pointers of the thread's rows, one plane above the next output
+#pragma unroll
+        for (int j = 0; j < RPT; j++)
+            op[j] = P.dst + ((size_t)(sg.zb + 2 * HW) * ny + (y0 + RPT * warp + j)) * nx + x0 + 2 * lane;
+        int zout = sg.zb + 2 * HW;
+        // B ring: plane p sits in slot (p - tmain) mod 3, so that the unrolled main loop sees
+        // compile-time slots
+        float *const B0 = Bbuf, *const B1 = Bbuf + NR * BP2, *const B2 = Bbuf + 2 * NR * BP2;
+        auto b_slot = [&](int p) -> float * { return Bbuf + ((p - tmain + 12) % 3) * (NR * BP2); };
+
+        // Z phase: the xy-filtered plane `zin` updates every partial sum and retires one output plane
+        auto zupdate = [&](const u64 *zin) {
+            zout--;  // output z = j + HW completes with this sample
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                op[j] -= plane_stride;
+                u64 prod[HW + 1];
+#pragma unroll
+                for (int m = 0; m <= HW; m++) prod[m] = mul2(zin[j], pk(P.taps.t[m], P.taps.t[m]), K);
+#pragma unroll
+                for (int a = W - 1; a >= 1; a--) acc[j][a] = add2(prod[a <= HW ? a : 2 * HW - a], acc[j][a - 1], K);
+                acc[j][0] = add2(prod[0], K.pz, K);
+            }
+            if (zout < sg.zb && zout >= sg.za) {
+#pragma unroll
+                for (int j = 0; j < RPT; j++) *reinterpret_cast<u64 *>(op[j]) = acc[j][W - 1];
+            }
+        };
+
+        // ---- software pipeline, ONE block barrier per step.  In step t:
+        //        TMA   plane t+PDA -> A ring                 (slot last read in step t-1)
+        //        patch x mirrors of A(t+3)                   (edge tiles; waits for its mbarrier)
+        //        Y, Z  B(t)                                  (patched in step t-1)
+        //        patch y mirrors of B(t+1)                   (produced in step t-1)
+        //        X     A(t+2) -> B(t+2)                      (waits for the plane's mbarrier)
+        //      every generic-proxy read is of data completed before this step's barrier; writers
+        //      and readers of a step touch different ring slots.
+        // slow steps: the pipeline fill (t < 0) and the tasks of the right-hand z mirror (stash /
+        // lerp: the first tmain tasks of a segment that reaches the top of the volume)
+        for (int t = -PDA; t < tmain; t++) {
+            __syncthreads();
+            if (producer) produce(t + PDA);
+            if (xedge && t + 3 >= 0 && t + 3 < ntask) {
+                wait_plane(t + 3);
+                xpatch(a_slot(t + 3));
+            }
+            if (t >= 0) {
+                u64 zin[RPT];
+                yphase(b_slot(t), zin);
+                const int mode = task_mode[t];
+                if ((mode & 3) == MODE_STASH) {
+#pragma unroll
+                    for (int j = 0; j < RPT; j++) prevY[j] = zin[j];
+                } else {  // MODE_LERP
+                    const int k = mode >> 2;
+                    const u64 f = pk(P.mz.f[k], P.mz.f[k]), omf = pk(P.mz.omf[k], P.mz.omf[k]);
+#pragma unroll
+                    for (int j = 0; j < RPT; j++) {
+                        const u64 cur = zin[j];
+                        zin[j] = add2(mul2(prevY[j], omf, K), mul2(cur, f, K), K);
+                        prevY[j] = cur;
+                    }
+                    zupdate(zin);
+                }
+            }
+            if (yedge && t + 1 >= 0 && t + 1 < ntask) ypatch(b_slot(t + 1));
+            if (t + 2 >= 0 && t + 2 < ntask) {
+                if (x_thread) wait_plane(t + 2);
+                xphase(a_slot(t + 2), b_slot(t + 2));
+            }
+        }
+        auto step = [&](int t, float *Bt, float *Bt1, float *Bt2) {
+            __syncthreads();
+            if (producer) produce(t + PDA);
+            if (xedge && t + 3 < ntask) {
+                wait_plane(t + 3);
+                xpatch(a_slot(t + 3));
+            }
+            u64 zin[RPT];
+            yphase(Bt, zin);
+            zupdate(zin);
+            if (yedge && t + 1 < ntask) ypatch(Bt1);
+            if (t + 2 < ntask) {
+                if (x_thread) wait_plane(t + 2);
+                xphase(a_slot(t + 2), Bt2);
+            }
+        };
+        for (int t = tmain; t < ntask;) {
+            step(t, B0, B1, B2);
+            if (++t >= ntask) break;
+            step(t, B1, B2, B0);
+            if (++t >= ntask) break;
+            step(t, B2, B0, B1);
+            if (++t >= ntask) break;
+        }
+        segbase += (unsigned)ntask;
+    }
+}
+
+template <int RPT>
+size_t tma_smem_bytes(int hw, int nz)
+{
+    size_t b = (size_t)TMA_NSA * tma_slot_bytes(hw, RPT) + tma_b_bytes(hw, RPT) + TMA_NSA * 8;
+    b += (size_t)(nz + 2 * hw + 4) * sizeof(short) + (size_t)(nz + 2 * hw + 4);
+    return ((b + 15) & ~(size_t)15) + 128;  // + alignment slack
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tma_encoder()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int HW, int RPT>
+int launch_tma(s3d_engine *e, const FusedParams &P, int grid, int nzbuf)
+{
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)P.nx, (cuuint64_t)P.ny, (cuuint64_t)nzbuf};
+    const cuuint64_t strides[2] = {(cuuint64_t)P.nx * 4, (cuuint64_t)P.nx * P.ny * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)tma_aw(HW), (cuuint32_t)(16 * RPT + 2 * HW), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = tma_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(P.src), dims, strides,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return s3d_fail(e, "fused blur: cuTensorMapEncodeTiled", cudaErrorInvalidValue, __FILE__, __LINE__);
+    TapPairs TP;
+    auto tap = [&](int a) { return a >= 0 && a < P.taps.width ? P.taps.t[a] : 0.0f; };
+    for (int k = 0; k <= MAXHW; k++) {
+        TP.e[k] = make_float2(tap(2 * k), tap(2 * k + 1));
+        TP.o[k] = make_float2(tap(2 * k - 1), tap(2 * k));
+    }
+    const size_t smem = tma_smem_bytes<RPT>(HW, P.nz);
+    static bool attr_set[64] = {};
+    if (!attr_set[e->device & 63]) {
+        S3D_CUDA(e, cudaFuncSetAttribute(k_blur_tma<HW, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[e->device & 63] = true;
+    }
+    k_blur_tma<HW, RPT><<<grid, NT, smem, e->stream>>>(map, P, TP);
+    S3D_LAUNCH_CHECK(e);
+    return 0;
+}
+
 size_t smem_bytes(int hw, int nz)
 {
     const int NR = TY + 2 * hw;
@@ -488,15 +927,22 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
     const int hw = taps.width / 2;
     const int nzr = ze - zb;
     if (nzr <= 0) return 0;
+    // which kernel: k_blur_tma (rows a multiple of 4 voxels, 16-byte aligned base -- what the tensor
+    // map needs) with a 64 x 64 tile for the narrow filters, else k_blur_fused
+    const bool use_tma = e->opt_blur_v1 == 0 && (nx & 3) == 0 && ((uintptr_t)src & 15) == 0 && nx >= tma_aw(hw) &&
+                         ny >= 32 + 2 * hw && tma_encoder() != nullptr && tma_smem_bytes<2>(hw, nz) <= 227 * 1024;
+    const int rpt = use_tma && hw <= e->opt_blur_rpt4_hw && hw <= 4 && ny >= 64 + 2 * hw &&
+                            tma_smem_bytes<4>(hw, nz) <= 227 * 1024 ? 4 : 2;
+    const int TYv = use_tma ? 16 * rpt : TY;
     // ---- work decomposition: columns (overlapping last tile) x balanced z ranges,
     //      computed once per volume size and cached in the engine -------------------------
     const SegTab *tab = nullptr;
     for (const auto &t : e->segtabs)
-        if (t.nx == nx && t.ny == ny && t.nz == nz && t.zb == zb && t.ze == ze) tab = &t;
+        if (t.nx == nx && t.ny == ny && t.nz == nz && t.zb == zb && t.ze == ze && t.ty == TYv) tab = &t;
     if (!tab) {
         std::vector<int> xs, ys;
         for (int x = 0; x < nx; x += TX) xs.push_back(std::min(x, nx - TX));
-        for (int y = 0; y < ny; y += TY) ys.push_back(std::min(y, ny - TY));
+        for (int y = 0; y < ny; y += TYv) ys.push_back(std::min(y, ny - TYv));
         const long ncol = (long)xs.size() * ys.size();
         const long total = ncol * nzr;
         const int grid = (int)std::min<long>(e->num_sms, std::max<long>(1, total / 16));
@@ -512,7 +958,7 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
             if (x0 - hw < 0) w *= e->blur_w[0];
             if (x0 + TX + hw > nx - 1) w *= e->blur_w[1];
             if (y0 - hw < 0) w *= e->blur_w[2];
-            if (y0 + TY + hw > ny - 1) w *= e->blur_w[3];
+            if (y0 + TYv + hw > ny - 1) w *= e->blur_w[3];
             wcol[c] = w;
             wsum += w * nzr;
         }
@@ -553,7 +999,7 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
         memcpy(host.data() + segs.size() * sizeof(Seg), start.data(), start.size() * sizeof(int));
         SegTab nt;
         nt.nx = nx, nt.ny = ny, nt.nz = nz, nt.grid = grid, nt.nseg = segs.size(), nt.d = nullptr;
-        nt.zb = zb, nt.ze = ze;
+        nt.zb = zb, nt.ze = ze, nt.ty = TYv;
         S3D_CUDA(e, cudaMalloc(&nt.d, need));
         S3D_CUDA(e, cudaMemcpyAsync(nt.d, host.data(), need, cudaMemcpyHostToDevice, e->stream));
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -582,6 +1028,21 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
     P.c_zero = 0.0f;
     P.dbg = e->d_blur_dbg;
     P.dbg_flags = e->opt_blur_flags;
+    if (use_tma) {
+#define S3D_TMA_CASE(H) \
+    case H: return rpt == 4 ? launch_tma<H, 4>(e, P, grid, nz) : launch_tma<H, 2>(e, P, grid, nz);
+        switch (hw) {
+            S3D_TMA_CASE(1)
+            S3D_TMA_CASE(2)
+            S3D_TMA_CASE(3)
+            S3D_TMA_CASE(4)
+        case 5: return launch_tma<5, 2>(e, P, grid, nz);
+        case 6: return launch_tma<6, 2>(e, P, grid, nz);
+        case 7: return launch_tma<7, 2>(e, P, grid, nz);
+        case 8: return launch_tma<8, 2>(e, P, grid, nz);
+        }
+#undef S3D_TMA_CASE
+    }
     const size_t smem = smem_bytes(hw, nz);
     switch (hw) {
     case 1: return launch<1>(e, P, grid, smem);

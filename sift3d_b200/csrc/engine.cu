@@ -241,6 +241,8 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "slab_timing")) e->opt_slab_timing = value;
     else if (!strcmp(name, "desc_path")) e->opt_desc_path = value & 7;
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
+    else if (!strcmp(name, "blur_v1")) e->opt_blur_v1 = value;
+    else if (!strcmp(name, "blur_rpt4_hw")) e->opt_blur_rpt4_hw = value;
     else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
     else if (!strcmp(name, "desc_norot")) e->opt_desc_norot = value;
