@@ -713,7 +713,7 @@ def main():
             tot_bytes += 8.0 * nvox
         ach = tot_bytes / (tot_ms * 1e-3) / 1e9
         traffic, traffic_per = blur_traffic()
-        roof = {"bound": "hbm", "kernel": "separable 3-D Gaussian blur (6 octave-0 filters of the pyramid)",
+        roof = {"bound": "hbm", "kernel": "separable 3-D Gaussian blur, k_blur_tma (TMA + mbarrier fed fused X/Y/Z pass; 6 octave-0 filters of the pyramid)",
                 "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 8.0 * nvox,
                 "per_filter": per}

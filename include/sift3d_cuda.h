@@ -226,7 +226,9 @@ int s3d_set_blur_mode(s3d_engine *e, int mode);
  * untrimmed -- tests only), "desc_occ" (4: CTAs per SM the descriptor kernel is compiled for; 3),
  * "desc_norot" (0; 1 = no lane-dependent vertex order in the descriptor scatter), "orient_batch"
  * (4: voxels the orientation kernel fetches ahead; 8 = line-aligned batches), "orient_v1" (0; 1 = the thread-per-candidate orientation kernel
- * instead of the grouped one: A/B measurements and tests), "dense_copy" (1: staged parallel copies to/from pageable host memory). */
+ * instead of the grouped one: A/B measurements and tests), "dense_copy" (1: staged parallel copies to/from pageable host memory),
+ * "blur_v1" (0; 1 = the round-1 fused Gaussian k_blur_fused (LDG fill) also where the TMA-fed k_blur_tma is eligible: A/B and
+ * tests), "blur_rpt4_hw" (3: widest filter half-width that takes k_blur_tma's 64 x 64 tile). */
 int s3d_set_option(s3d_engine *e, const char *name, int value);
 /* Debug: per-CTA {start, end clock, SM id, steps} of the last fused blur (after option "blur_dbg"). */
 int s3d_debug_read(s3d_engine *e, void *host, size_t bytes);

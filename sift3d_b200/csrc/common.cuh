@@ -90,7 +90,7 @@ struct s3d_engine {
     double blur_w[4] = {1.05, 1.10, 1.05, 1.10};  // per-plane cost of edge columns (left,right,top,bottom)
     int opt_blur_flags = 0;  // timing experiments only (results wrong when non-zero)
     int opt_blur_v1 = 0;     // 1: k_blur_fused (round 1, LDG fill) instead of k_blur_tma (A/B, tests)
-    int opt_blur_rpt4_hw = 4;  // widest half-width that takes the 64 x 64 tile of k_blur_tma
+    int opt_blur_rpt4_hw = 3;  // widest half-width that takes the 64 x 64 tile of k_blur_tma (w = 9 measured slower with it)
 
     // pyramid
     int noct = 0, K = 0, nlev_g = 0, nlev_d = 0;

@@ -24,6 +24,7 @@ class Engine:
         L.s3d_engine_launch_count.argtypes = [C.c_void_p]
         L.s3d_engine_launch_count.restype = C.c_longlong
         L.s3d_set_blur_mode.argtypes = [C.c_void_p, C.c_int]
+        L.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.s3d_dev_alloc.argtypes = [C.c_void_p, C.c_size_t]
         L.s3d_dev_alloc.restype = C.c_void_p
         L.s3d_dev_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -55,6 +56,9 @@ class Engine:
 
     def sync(self):
         self._check(self.L.s3d_engine_sync(self.h), "sync")
+
+    def set_option(self, name: str, value: int):
+        self._check(self.L.s3d_set_option(self.h, name.encode(), int(value)), f"set_option {name}")
 
     def launches(self) -> int:
         return int(self.L.s3d_engine_launch_count(self.h))

@@ -167,6 +167,38 @@ def test_generic_and_fused_blur_agree_with_oracle(b200_lib, oracle_cls):
     eng.close()
 
 
+@pytest.mark.gpu
+def test_tma_blur_agrees_with_oracle_and_with_the_ldg_kernel(b200_lib, oracle_cls):
+    """k_blur_tma (TMA + mbarrier fill, tap-pair X phase; both tile heights) on shapes whose rows
+    are a multiple of 4 voxels and wide enough for its box: tiles that touch every edge, overlapping
+    last tiles, interior tiles, every filter half-width 1..8.  Bit-exact against the oracle and
+    against k_blur_fused (option blur_v1)."""
+    from sift3d_b200.engine_api import Engine
+    orc = oracle_cls()
+    rng = np.random.default_rng(11)
+    eng = Engine()
+    sig = [1.6 * 2 ** (k / 3.0) for k in range(-1, 5)]
+    sigmas = [np.sqrt(sig[0] ** 2 - 1.15 ** 2)] + [np.sqrt(sig[i + 1] ** 2 - sig[i] ** 2)
+                                                   for i in range(5)] + [2.2, 0.3]
+    try:
+        for shape in [(40, 96, 84), (19, 49, 88), (33, 80, 80), (37, 100, 132), (30, 200, 260)]:
+            vol = (rng.random(shape, dtype=np.float32) - 0.25).astype(np.float32)  # some negative samples
+            for sg in sigmas:
+                taps = orc.gauss_taps(sg)
+                want = orc.blur(vol, taps, (1.0, 1.0, 1.0))
+                eng.set_option("blur_v1", 1)
+                old = eng.blur(vol, taps)
+                assert np.array_equal(old.view(np.uint32), want.view(np.uint32)), (shape, len(taps), "v1")
+                eng.set_option("blur_v1", 0)
+                for rpt4 in (3, 0):
+                    eng.set_option("blur_rpt4_hw", rpt4)
+                    got = eng.blur(vol, taps)
+                    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+                        (shape, len(taps), rpt4, np.abs(got - want).max())
+    finally:
+        eng.close()
+
+
 def test_error_behaviour_matches_reference(b200_lib):
     from sift3d_b200 import capi
     L = b200_lib.lib

@@ -32,7 +32,7 @@ def main():
         raw = out.parent / f"r02_ncu_blur_w{width}.csv"
         cmd = ["ncu", "--csv", "--clock-control", "none", "--metrics",
                "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
-               "-k", "regex:k_blur_fused", "-s", "2", "-c", "1", "--log-file", str(raw),
+               "-k", "regex:k_blur_(fused|tma)", "-s", "2", "-c", "1", "--log-file", str(raw),
                sys.executable, str(REPO / "tools" / "run_blur.py"), str(n), str(which), "3"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
         vals = {}

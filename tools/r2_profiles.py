@@ -84,7 +84,11 @@ def main():
             ("r2_orient_group.ncu-rep", "r02_ncu_orient_group.txt", "k_orient_group (one batch in flight; 256^3 volume, 23.4k candidates)",
              "ncu --set full --clock-control none --import-source on -k regex:k_orient_group -c 1 python tools/run_desc.py 256"),
             ("r2_blur_f0.ncu-rep", "r02_ncu_blur_w5.txt", "k_blur_fused<2> (w = 5) at 512^3", "ncu --set full ... python tools/run_blur.py 512 0 3"),
-            ("r2_blur_f2.ncu-rep", "r02_ncu_blur_w9.txt", "k_blur_fused<4> (w = 9) at 512^3", "ncu --set full ... python tools/run_blur.py 512 2 3")]
+            ("r2_blur_f2.ncu-rep", "r02_ncu_blur_w9.txt", "k_blur_fused<4> (w = 9) at 512^3", "ncu --set full ... python tools/run_blur.py 512 2 3"),
+            ("r2_blur_tma_f0.ncu-rep", "r02_ncu_blur_tma_w5.txt", "k_blur_tma<2,4> (w = 5, TMA fill, 64 x 64 tile) at 512^3",
+             "ncu --set full --clock-control none --import-source on -k regex:k_blur_tma -s 2 -c 1 python tools/run_blur.py 512 0 3"),
+            ("r2_blur_tma_f5.ncu-rep", "r02_ncu_blur_tma_w17.txt", "k_blur_tma<8,2> (w = 17, TMA fill, 64 x 32 tile) at 512^3",
+             "ncu --set full --clock-control none --import-source on -k regex:k_blur_tma -s 2 -c 1 python tools/run_blur.py 512 5 3")]
     for rep, out, title, cmd in jobs:
         if not (G / rep).exists():
             print("missing", rep)
@@ -93,7 +97,7 @@ def main():
         (P / out).write_text("\n".join(lines) + "\n")
         print("wrote", out)
     lines = ["SASS opcode histograms of the product kernels (cuobjdump -sass sift3d_b200/lib/*.o; static counts)", ""]
-    for obj, pat in (("keypoint.o", r"k_descriptor3ILi4ELb1|k_orient_group|k_gradient"), ("blur_fused.o", r"k_blur_fusedILi(2|8)E")):
+    for obj, pat in (("keypoint.o", r"k_descriptor3ILi4ELb1|k_orient_group|k_gradient"), ("blur_fused.o", r"k_blur_fusedILi(2|8)ELb1|k_blur_tmaILi(2ELi4|8ELi2)")):
         for fn, h in sass_hist(REPO / "sift3d_b200" / "lib" / obj, pat).items():
             lines.append(f"{obj}: {fn}")
             lines.append("  " + ", ".join(f"{op} {n}" for op, n in h.most_common(28)))
