@@ -228,7 +228,8 @@ int s3d_set_blur_mode(s3d_engine *e, int mode);
  * (4: voxels the orientation kernel fetches ahead; 8 = line-aligned batches), "orient_v1" (0; 1 = the thread-per-candidate orientation kernel
  * instead of the grouped one: A/B measurements and tests), "dense_copy" (1: staged parallel copies to/from pageable host memory),
  * "blur_v1" (0; 1 = the round-1 fused Gaussian k_blur_fused (LDG fill) also where the TMA-fed k_blur_tma is eligible: A/B and
- * tests), "blur_rpt4_hw" (3: widest filter half-width that takes k_blur_tma's 64 x 64 tile). */
+ * tests), "blur_rpt4_hw" (3: widest filter half-width that takes k_blur_tma's 64 x 64 tile), "blur_w0" .. "blur_w3" (permille: per-plane cost of a
+ * left / right / top / bottom edge column of the fused blur relative to an interior one; balances the persistent CTAs' z ranges). */
 int s3d_set_option(s3d_engine *e, const char *name, int value);
 /* Debug: per-CTA {start, end clock, SM id, steps} of the last fused blur (after option "blur_dbg"). */
 int s3d_debug_read(s3d_engine *e, void *host, size_t bytes);

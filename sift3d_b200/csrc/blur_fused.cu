@@ -950,15 +950,19 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
         // critical path of every step); measured on B200 (tools/blur_dbg.py, cycles/step relative
         // to an interior column): left 1.11, right 1.30, top 1.06, bottom 1.19.  The z ranges are
         // balanced by cost so that all persistent CTAs finish together.
+        // the mirror patches grow with the filter: measured with k_blur_tma at 512^3
+        // (profiles/r02_blur_ab.txt), w >= 13 is fastest with the larger set, w <= 11 with the smaller
+        static const double bw_wide[4] = {1.15, 1.30, 1.10, 1.25};
+        const double *bw = (use_tma && hw >= 6 && !e->blur_w_user) ? bw_wide : e->blur_w;
         std::vector<double> wcol(ncol);
         double wsum = 0;
         for (long c = 0; c < ncol; c++) {
             const int x0 = xs[c % xs.size()], y0 = ys[c / xs.size()];
             double w = 1.0;
-            if (x0 - hw < 0) w *= e->blur_w[0];
-            if (x0 + TX + hw > nx - 1) w *= e->blur_w[1];
-            if (y0 - hw < 0) w *= e->blur_w[2];
-            if (y0 + TYv + hw > ny - 1) w *= e->blur_w[3];
+            if (x0 - hw < 0) w *= bw[0];
+            if (x0 + TX + hw > nx - 1) w *= bw[1];
+            if (y0 - hw < 0) w *= bw[2];
+            if (y0 + TYv + hw > ny - 1) w *= bw[3];
             wcol[c] = w;
             wsum += w * nzr;
         }

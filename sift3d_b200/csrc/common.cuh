@@ -88,6 +88,7 @@ struct s3d_engine {
     int opt_desc_occ = 4;   // CTAs per SM k_descriptor2 is compiled for (3 or 4)
     int opt_desc_path = 0;  // test hook: force a fixed-point path of k_descriptor2 (0 = automatic)
     double blur_w[4] = {1.05, 1.10, 1.05, 1.10};  // per-plane cost of edge columns (left,right,top,bottom)
+    bool blur_w_user = false;  // set through options blur_w0..3: then used for every filter width
     int opt_blur_flags = 0;  // timing experiments only (results wrong when non-zero)
     int opt_blur_v1 = 0;     // 1: k_blur_fused (round 1, LDG fill) instead of k_blur_tma (A/B, tests)
     int opt_blur_rpt4_hw = 3;  // widest half-width that takes the 64 x 64 tile of k_blur_tma (w = 9 measured slower with it)
