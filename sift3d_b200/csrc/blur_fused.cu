@@ -645,12 +645,17 @@ __global__ void __launch_bounds__(NT, 1)
             }
         };
 
-        // ---- mirror patches (edge tiles only; each runs a step before its consumer) ---------------
+        // ---- mirror patches (edge tiles only; each runs a step before its consumer).  The warps
+        //      without X items do them: they have half the work of the others in every step, so
+        //      the patches stay off the critical path of the step ---------------------------------------
+        constexpr int PT0 = ((NXI + 31) / 32) * 32, PTN = NT - PT0;  // first patch thread, their number
+        static_assert(PTN >= 64, "at least two warps without X items");
+        const bool patch_thread = tid >= PT0;
         auto xpatch = [&](float *Ep) {  // columns outside [0, nx-1)
             const int nl = x0 - HW < 0 ? HW - x0 : 0;  // x = x0-HW .. -1
             const int nrt = x0 + TX + HW > nx - 1 ? x0 + TX + HW - (nx - 1) : 0;  // x = nx-1 ..
             const int ncol = nl + nrt;
-            for (int e = tid; e < NR * ncol; e += NT) {
+            for (int e = tid - PT0; e < NR * ncol; e += PTN) {
                 const int r = e / ncol, c = e - r * ncol;
                 float v;
                 int dc;
@@ -670,7 +675,7 @@ __global__ void __launch_bounds__(NT, 1)
         auto ypatch = [&](float *Bp) {  // rows of B outside [0, ny-1)
             const int nt_ = y0 - HW < 0 ? HW - y0 : 0;
             const int nb_ = y0 + TYT + HW > ny - 1 ? y0 + TYT + HW - (ny - 1) : 0;
-            for (int e = tid; e < (nt_ + nb_) * TX; e += NT) {
+            for (int e = tid - PT0; e < (nt_ + nb_) * TX; e += PTN) {
                 const int rr = e / TX, x = e - rr * TX;
                 if (rr < nt_) {
                     const int y = y0 - HW + rr;  // < 0: copy of row -y
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(NT, 1)
         for (int t = -PDA; t < tmain; t++) {
             __syncthreads();
             if (producer) produce(t + PDA);
-            if (xedge && t + 3 >= 0 && t + 3 < ntask) {
+            if (xedge && patch_thread && t + 3 >= 0 && t + 3 < ntask) {
                 wait_plane(t + 3);
                 xpatch(a_slot(t + 3));
             }
@@ -758,7 +763,7 @@ __global__ void __launch_bounds__(NT, 1)
                     zupdate(zin);
                 }
             }
-            if (yedge && t + 1 >= 0 && t + 1 < ntask) ypatch(b_slot(t + 1));
+            if (yedge && patch_thread && t + 1 >= 0 && t + 1 < ntask) ypatch(b_slot(t + 1));
             if (t + 2 >= 0 && t + 2 < ntask) {
                 if (x_thread) wait_plane(t + 2);
                 xphase(a_slot(t + 2), b_slot(t + 2));
@@ -767,14 +772,14 @@ __global__ void __launch_bounds__(NT, 1)
         auto step = [&](int t, float *Bt, float *Bt1, float *Bt2) {
             __syncthreads();
             if (producer) produce(t + PDA);
-            if (xedge && t + 3 < ntask) {
+            if (xedge && patch_thread && t + 3 < ntask) {
                 wait_plane(t + 3);
                 xpatch(a_slot(t + 3));
             }
             u64 zin[RPT];
             yphase(Bt, zin);
             zupdate(zin);
-            if (yedge && t + 1 < ntask) ypatch(Bt1);
+            if (yedge && patch_thread && t + 1 < ntask) ypatch(Bt1);
             if (t + 2 < ntask) {
                 if (x_thread) wait_plane(t + 2);
                 xphase(a_slot(t + 2), Bt2);
@@ -938,7 +943,7 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
     //      computed once per volume size and cached in the engine -------------------------
     const SegTab *tab = nullptr;
     for (const auto &t : e->segtabs)
-        if (t.nx == nx && t.ny == ny && t.nz == nz && t.zb == zb && t.ze == ze && t.ty == TYv) tab = &t;
+        if (t.nx == nx && t.ny == ny && t.nz == nz && t.zb == zb && t.ze == ze && t.ty == TYv && t.hw == hw) tab = &t;
     if (!tab) {
         std::vector<int> xs, ys;
         for (int x = 0; x < nx; x += TX) xs.push_back(std::min(x, nx - TX));
@@ -950,10 +955,11 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
         // critical path of every step); measured on B200 (tools/blur_dbg.py, cycles/step relative
         // to an interior column): left 1.11, right 1.30, top 1.06, bottom 1.19.  The z ranges are
         // balanced by cost so that all persistent CTAs finish together.
-        // the mirror patches grow with the filter: measured with k_blur_tma at 512^3
-        // (profiles/r02_blur_ab.txt), w >= 13 is fastest with the larger set, w <= 11 with the smaller
-        static const double bw_wide[4] = {1.15, 1.30, 1.10, 1.25};
-        const double *bw = (use_tma && hw >= 6 && !e->blur_w_user) ? bw_wide : e->blur_w;
+        // cost of an edge column relative to an interior one (left, right, top, bottom): the mirror
+        // patches grow with the filter.  Measured with k_blur_tma at 512^3 (profiles/r02_blur_ab.txt):
+        // the fastest of five weight sets per filter width
+        static const double bw_tma[3][4] = {{1.02, 1.04, 1.02, 1.04}, {1.01, 1.02, 1.01, 1.02}, {1.10, 1.20, 1.10, 1.20}};
+        const double *bw = (use_tma && !e->blur_w_user) ? bw_tma[hw <= 3 ? 0 : hw == 4 ? 1 : 2] : e->blur_w;
         std::vector<double> wcol(ncol);
         double wsum = 0;
         for (long c = 0; c < ncol; c++) {
@@ -969,18 +975,33 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
         std::vector<Seg> segs;
         std::vector<int> start(grid + 1, 0);
         {
+            // The work list is cut into `grid` consecutive shares of equal cost.  Its order decides what
+            // runs at the same time: CTA b starts at list position b * quota, so neighbouring columns
+            // are (quota mod piece length) planes apart in z, and their shared halo columns / rows hit
+            // in L2 only when that is well below the ~120 planes of 512 x 512 floats the L2 holds.
+            // With one piece per column and fewer columns than CTAs (the 64 x 64 tile: 64 columns,
+            // quota 221 of 512 planes) they are 221 planes apart and every halo is fetched from DRAM
+            // again (measured 1.30 x the algorithmic traffic); cutting z into S slabs and listing the
+            // pieces slab by slab brings the offset to |quota - nz / S| (S = 2: 35 planes).
+            const int S = e->opt_blur_slabs > 0 ? e->opt_blur_slabs
+                                                : (int)std::max<long>(1, std::min<long>(std::lround((double)grid / (double)ncol), nzr / (4 * hw + 4)));
+            const long npiece = ncol * S;
+            auto piece_lo = [&](long pc) { return zb + (int)((long)nzr * (pc / ncol) / S); };
+            auto piece_hi = [&](long pc) { return zb + (int)((long)nzr * (pc / ncol + 1) / S); };
             const double quota = wsum / grid;
-            long col = 0;
-            int z = zb;
+            long pc = 0;
+            int z = piece_lo(0);
             for (int b = 0; b < grid; b++) {
                 start[b] = (int)segs.size();
                 double need = quota;
-                while (col < ncol && (need > 1e-9 || b == grid - 1)) {
+                while (pc < npiece && (need > 1e-9 || b == grid - 1)) {
+                    const long col = pc % ncol;
+                    const int pze = piece_hi(pc);
                     const double per = wcol[col];  // halo planes ignored
-                    int take = (b == grid - 1) ? ze - z : (int)std::min<double>(ze - z, std::ceil(need / per - 1e-9));
+                    int take = (b == grid - 1) ? pze - z : (int)std::min<double>(pze - z, std::ceil(need / per - 1e-9));
                     if (take <= 0) break;
-                    // avoid leaving a sliver shorter than the halo at the end of a column
-                    if (ze - (z + take) > 0 && ze - (z + take) < 2 * hw && b != grid - 1) take = ze - z;
+                    // avoid leaving a sliver shorter than the halo at the end of a piece
+                    if (pze - (z + take) > 0 && pze - (z + take) < 2 * hw && b != grid - 1) take = pze - z;
                     Seg sg;
                     sg.x0 = xs[col % xs.size()];
                     sg.y0 = ys[col / xs.size()];
@@ -989,9 +1010,9 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
                     segs.push_back(sg);
                     need -= take * per;
                     z += take;
-                    if (z >= ze) {
-                        z = zb;
-                        col++;
+                    if (z >= pze) {
+                        pc++;
+                        if (pc < npiece) z = piece_lo(pc);
                     }
                 }
             }
@@ -1003,7 +1024,7 @@ int s3d_blur_fused_zrange(s3d_engine *e, const float *src, float *dst, int nx, i
         memcpy(host.data() + segs.size() * sizeof(Seg), start.data(), start.size() * sizeof(int));
         SegTab nt;
         nt.nx = nx, nt.ny = ny, nt.nz = nz, nt.grid = grid, nt.nseg = segs.size(), nt.d = nullptr;
-        nt.zb = zb, nt.ze = ze, nt.ty = TYv;
+        nt.zb = zb, nt.ze = ze, nt.ty = TYv, nt.hw = hw;
         S3D_CUDA(e, cudaMalloc(&nt.d, need));
         S3D_CUDA(e, cudaMemcpyAsync(nt.d, host.data(), need, cudaMemcpyHostToDevice, e->stream));
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));

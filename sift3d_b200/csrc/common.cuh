@@ -52,6 +52,7 @@ struct MeshDev {
 struct SegTab {  // cached work decomposition of the fused blur for one volume size / z range
     int nx, ny, nz, grid;
     int zb, ze;  // output planes [zb, ze) (0, nz for a whole volume)
+    int hw;      // filter half-width (halo slivers and edge-column weights depend on it)
     int ty;      // tile height the table was cut for (32: k_blur_fused / k_blur_tma<.,2>, 64: k_blur_tma<.,4>)
     void *d;
     size_t nseg;
@@ -88,6 +89,7 @@ struct s3d_engine {
     int opt_desc_occ = 4;   // CTAs per SM k_descriptor2 is compiled for (3 or 4)
     int opt_desc_path = 0;  // test hook: force a fixed-point path of k_descriptor2 (0 = automatic)
     double blur_w[4] = {1.05, 1.10, 1.05, 1.10};  // per-plane cost of edge columns (left,right,top,bottom)
+    int opt_blur_slabs = 0;    // z slabs of the fused blur's work list (0 = automatic; A/B only)
     bool blur_w_user = false;  // set through options blur_w0..3: then used for every filter width
     int opt_blur_flags = 0;  // timing experiments only (results wrong when non-zero)
     int opt_blur_v1 = 0;     // 1: k_blur_fused (round 1, LDG fill) instead of k_blur_tma (A/B, tests)

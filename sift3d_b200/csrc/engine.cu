@@ -243,7 +243,13 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "blur_flags")) e->opt_blur_flags = value;
     else if (!strcmp(name, "blur_v1")) e->opt_blur_v1 = value;
     else if (!strcmp(name, "blur_rpt4_hw")) e->opt_blur_rpt4_hw = value;
-    else if (!strncmp(name, "blur_w", 6) && name[6] >= '0' && name[6] <= '3' && !name[7]) {
+    else if (!strcmp(name, "blur_slabs")) {
+        e->opt_blur_slabs = value;
+        cudaStreamSynchronize(e->stream);
+        for (auto &t : e->segtabs)
+            if (t.d) cudaFree(t.d);
+        e->segtabs.clear();
+    } else if (!strncmp(name, "blur_w", 6) && name[6] >= '0' && name[6] <= '3' && !name[7]) {
         // per-plane cost of an edge column relative to an interior one, in permille (left, right,
         // top, bottom): the persistent CTAs' z ranges are balanced with it; cached tables are dropped
         e->blur_w[name[6] - '0'] = value * 1e-3;
