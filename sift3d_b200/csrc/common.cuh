@@ -154,6 +154,13 @@ struct s3d_engine {
     cudaEvent_t dense_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double dense_ms[3] = {-1.0, -1.0, -1.0};  // upload, kernels, download of the last dense call
     int opt_dense_copy = 1;  // 1 = staged parallel download, 0 = plain cudaMemcpy into pageable memory
+    // chunk pipeline between pageable host memory and the device (engine.cu: PipeJob)
+    void *pipe_buf = nullptr;
+    size_t pipe_cap = 0;
+    std::vector<cudaEvent_t> pipe_ev;
+    int opt_copy_pipe = 0;        // 1 = whole-chunk workers through a ring of small pinned slots
+    int opt_pipe_chunk_kb = 4096;
+    int opt_pipe_slots = 8;
 
     // descriptor scratch
     s3d_keypoint *d_kp_in = nullptr;

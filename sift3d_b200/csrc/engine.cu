@@ -4,9 +4,15 @@
 // SIFT3D object.  Host code (plain C, sift3d_b200/host/) owns parameters, filter
 // design and the reference-compatible structs; everything per-voxel happens here.
 #include "common.cuh"
+#include "host_pipe.h"
 
-#include <thread>
+#include <sched.h>
+
+#include <atomic>
 #include <ctime>
+#include <functional>
+#include <memory>
+#include <thread>
 
 #include <cmath>
 #include <cstdlib>
@@ -167,6 +173,9 @@ int s3d_engine_create(s3d_engine **out, int device)
     // tuning / A-B switches for the tools (same as s3d_set_option)
     if (const char *v = getenv("S3D_BLUR_MODE")) e->blur_mode = atoi(v);
     if (const char *v = getenv("S3D_DENSE_COPY")) e->opt_dense_copy = atoi(v);
+    if (const char *v = getenv("S3D_COPY_PIPE")) e->opt_copy_pipe = atoi(v);
+    if (const char *v = getenv("S3D_PIPE_CHUNK_KB")) e->opt_pipe_chunk_kb = atoi(v);
+    if (const char *v = getenv("S3D_PIPE_SLOTS")) e->opt_pipe_slots = atoi(v);
     if (const char *v = getenv("S3D_DESC_OCC")) e->opt_desc_occ = atoi(v);
     if (const char *v = getenv("S3D_DESC_NOROT")) e->opt_desc_norot = atoi(v);
     if (const char *v = getenv("S3D_ORIENT_BATCH")) e->opt_orient_batch = atoi(v);
@@ -197,6 +206,8 @@ void s3d_engine_destroy(s3d_engine *e)
         if (p) cudaFree(p);
     for (void *p : e->stage)
         if (p) cudaFreeHost(p);
+    if (e->pipe_buf) cudaFreeHost(e->pipe_buf);
+    for (cudaEvent_t ev : e->pipe_ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->dense_ev)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->slab_ev) cudaEventDestroy(ev);
@@ -260,6 +271,9 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
         e->segtabs.clear();
     }
     else if (!strcmp(name, "dense_copy")) e->opt_dense_copy = value;
+    else if (!strcmp(name, "copy_pipe")) e->opt_copy_pipe = value;
+    else if (!strcmp(name, "pipe_chunk_kb")) e->opt_pipe_chunk_kb = value;
+    else if (!strcmp(name, "pipe_slots")) e->opt_pipe_slots = value;
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
     else if (!strcmp(name, "desc_norot")) e->opt_desc_norot = value;
     else if (!strcmp(name, "orient_batch")) e->opt_orient_batch = value;
@@ -789,84 +803,68 @@ static int stage_ensure(s3d_engine *e, size_t bytes)
 // threads per 32 MB chunk cost ~3 ms per 512 MB volume).  One team per process, created on
 // first use; its size is the core count divided by the ranks sharing the host
 // ($LOCAL_WORLD_SIZE, set by torchrun), at most 8 ($S3D_COPY_THREADS overrides).
-namespace {
-class HostTeam {
-public:
-    static HostTeam &get()
-    {
-        static HostTeam t;
-        return t;
-    }
-    // memcpy split into page-aligned shares; the caller takes share 0
-    void copy(char *d, const char *src, size_t len)
-    {
-        std::unique_lock<std::mutex> lk(call_mu_);  // one copy at a time (engines share the team)
-        const unsigned n = (unsigned)workers_.size() + 1;
-        const size_t part = ((len + n - 1) / n + 4095) & ~(size_t)4095;
-        {
-            std::lock_guard<std::mutex> g(mu_);
-            d_ = d, s_ = src, len_ = len, part_ = part;
-            pending_ = (int)workers_.size();
-            gen_++;
-        }
-        cv_.notify_all();
-        memcpy(d, src, std::min(part, len));
-        std::unique_lock<std::mutex> g(mu_);
-        done_.wait(g, [&] { return pending_ == 0; });
-    }
-
-private:
-    HostTeam()
-    {
-        unsigned hw = std::thread::hardware_concurrency();
-        if (hw < 1) hw = 1;
-        unsigned share = 1;
-        if (const char *v = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(v));
-        unsigned n = std::max(2u, std::min(8u, hw / share));  // measured on a 16-core host: 8 beats 16
-        if (const char *v = getenv("S3D_COPY_THREADS")) n = (unsigned)std::max(1, atoi(v));
-        for (unsigned t = 1; t < n; t++) workers_.emplace_back([this, t] { run(t); });
-    }
-    ~HostTeam()
-    {
-        {
-            std::lock_guard<std::mutex> g(mu_);
-            stop_ = true;
-            gen_++;
-        }
-        cv_.notify_all();
-        for (auto &w : workers_) w.join();
-    }
-    void run(unsigned t)
-    {
-        unsigned long long seen = 0;
-        for (;;) {
-            std::unique_lock<std::mutex> g(mu_);
-            cv_.wait(g, [&] { return gen_ != seen; });
-            seen = gen_;
-            if (stop_) return;
-            char *d = d_;
-            const char *s = s_;
-            const size_t len = len_, part = part_;
-            g.unlock();
-            const size_t lo = (size_t)t * part;
-            if (lo < len) memcpy(d + lo, s + lo, std::min(part, len - lo));
-            g.lock();
-            if (--pending_ == 0) done_.notify_one();
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::mutex mu_, call_mu_;
-    std::condition_variable cv_, done_;
-    unsigned long long gen_ = 0;
-    int pending_ = 0;
-    bool stop_ = false;
-    char *d_ = nullptr;
-    const char *s_ = nullptr;
-    size_t len_ = 0, part_ = 0;
-};
-}  // namespace
-
 static void par_memcpy(char *d, const char *src, size_t len) { HostTeam::get().copy(d, src, len); }
+
+// Pinned ring + events of the chunk pipeline (kept between calls).
+static int pipe_ensure(s3d_engine *e, size_t bytes, size_t ns)
+{
+    if (e->pipe_cap < bytes) {
+        if (e->pipe_buf) cudaFreeHost(e->pipe_buf);
+        e->pipe_buf = nullptr;
+        e->pipe_cap = 0;
+        S3D_CUDA(e, cudaHostAlloc(&e->pipe_buf, bytes, cudaHostAllocDefault));
+        e->pipe_cap = bytes;
+    }
+    while (e->pipe_ev.size() < ns) {
+        cudaEvent_t ev = nullptr;
+        S3D_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->pipe_ev.push_back(ev);
+    }
+    return 0;
+}
+
+// One transfer through the chunk pipeline (see PipeJob): dir 0 = pageable host -> device,
+// dir 1 = device -> pageable host.  Returns with the transfer complete.
+static int pipe_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t bytes)
+{
+    const size_t ch = (size_t)std::max(256, e->opt_pipe_chunk_kb) << 10;
+    const size_t ns = (size_t)std::min(64, std::max(2, e->opt_pipe_slots));
+    if (pipe_ensure(e, ch * ns, ns)) return -1;
+    PipeJob J;
+    J.dir = dir;
+    J.host = (char *)host;
+    J.slots = (char *)e->pipe_buf;
+    J.bytes = bytes, J.ch = ch, J.ns = ns;
+    J.nch = (bytes + ch - 1) / ch;
+    std::unique_ptr<std::atomic<unsigned char>[]> flags(new std::atomic<unsigned char>[J.nch]);
+    for (size_t c = 0; c < J.nch; c++) flags[c].store(0, std::memory_order_relaxed);
+    J.flag = flags.get();
+    cudaError_t ce = cudaSuccess;
+    cudaStream_t st = e->stream;
+    // issue the DMA of chunk c (in order, on the engine's stream) / poll the event of a slot
+    auto issue = [&](size_t c) {
+        char *slot = J.slots + (c % ns) * ch;
+        char *d = (char *)dev + c * ch;
+        const size_t len = std::min(ch, bytes - c * ch);
+        ce = dir == 0 ? cudaMemcpyAsync(d, slot, len, cudaMemcpyHostToDevice, st)
+                      : cudaMemcpyAsync(slot, d, len, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaEventRecord(e->pipe_ev[c % ns], st);
+        return ce == cudaSuccess;
+    };
+    auto poll = [&](size_t c) {  // 1 done, 0 in flight, -1 error
+        const cudaError_t q = cudaEventQuery(e->pipe_ev[c % ns]);
+        if (q == cudaSuccess) return 1;
+        if (q == cudaErrorNotReady) return 0;
+        ce = q;
+        return -1;
+    };
+    s3d_pipe_run(J, issue, poll);
+    const cudaError_t cs = cudaStreamSynchronize(st);  // the last DMAs; the ring is free again
+    cudaGetLastError();  // cudaErrorNotReady of the polls is not an error
+    if (ce == cudaSuccess) ce = cs;
+    if (ce != cudaSuccess) return s3d_fail(e, dir ? "pipelined download" : "pipelined upload", ce, __FILE__, __LINE__);
+    return 0;
+}
 
 // Device -> PAGEABLE host memory (the caller's malloc'ed Image, SURVEY.md 8b ownership rule).
 // A plain cudaMemcpy stages through the driver's bounce buffer and copies out on one core; here
@@ -881,6 +879,7 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));
         return 0;
     }
+    if (e->opt_copy_pipe) return pipe_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
@@ -914,6 +913,7 @@ static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes
         S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
         return 0;
     }
+    if (e->opt_copy_pipe) return pipe_transfer(e, 0, dev, const_cast<void *>(host), bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
