@@ -227,6 +227,8 @@ int s3d_set_blur_mode(s3d_engine *e, int mode);
  * "desc_norot" (0; 1 = no lane-dependent vertex order in the descriptor scatter), "orient_batch"
  * (4: voxels the orientation kernel fetches ahead; 8 = line-aligned batches), "orient_v1" (0; 1 = the thread-per-candidate orientation kernel
  * instead of the grouped one: A/B measurements and tests), "dense_copy" (1: staged parallel copies to/from pageable host memory),
+ * "copy_pipe" (how those staged copies run: 0 = one chunk at a time split over the host threads, 1 = every thread moves whole chunks
+ * through a ring of "pipe_slots" (8) pinned slots of "pipe_chunk_kb" (4096) KB: csrc/host_pipe.h),
  * "blur_v1" (0; 1 = the round-1 fused Gaussian k_blur_fused (LDG fill) also where the TMA-fed k_blur_tma is eligible: A/B and
  * tests), "blur_rpt4_hw" (3: widest filter half-width that takes k_blur_tma's 64 x 64 tile), "blur_w0" .. "blur_w3" (permille: per-plane cost of a
  * left / right / top / bottom edge column of the fused blur relative to an interior one; balances the persistent CTAs' z ranges). */
@@ -237,6 +239,10 @@ void *s3d_dev_alloc(s3d_engine *e, size_t bytes);
 void s3d_dev_free(s3d_engine *e, void *p);
 int s3d_memcpy_h2d(s3d_engine *e, void *dev, const void *host, size_t bytes);
 int s3d_memcpy_d2h(s3d_engine *e, void *host, const void *dev, size_t bytes);
+/* Tests: host_src -> device -> host_dst through the paths the library takes for a caller's
+ * PAGEABLE buffers (im_copy_data of the input Image, imutil.c:1895; the dense result written into
+ * the caller's Image, sift.c:2375-2380): staged copies for >= 32 / 64 MB, see option "copy_pipe". */
+int s3d_host_roundtrip(s3d_engine *e, const void *host_src, void *host_dst, size_t bytes);
 
 #ifdef __cplusplus
 }

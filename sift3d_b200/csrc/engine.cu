@@ -1116,4 +1116,16 @@ int s3d_memcpy_d2h(s3d_engine *e, void *host, const void *dev, size_t bytes)
     return 0;
 }
 
+int s3d_host_roundtrip(s3d_engine *e, const void *host_src, void *host_dst, size_t bytes)
+{
+    DeviceGuard guard(e->device);
+    void *d = nullptr;
+    S3D_CUDA(e, cudaMalloc(&d, bytes));
+    int rc = h2d_pageable(e, d, host_src, bytes);
+    if (!rc) rc = d2h_pageable(e, host_dst, d, bytes);
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    return rc;
+}
+
 }  // extern "C"

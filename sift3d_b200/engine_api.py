@@ -31,6 +31,7 @@ class Engine:
         L.s3d_dev_free.restype = None
         L.s3d_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.s3d_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.s3d_host_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.s3d_blur_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                       C.c_void_p]
@@ -56,6 +57,14 @@ class Engine:
 
     def sync(self):
         self._check(self.L.s3d_engine_sync(self.h), "sync")
+
+    def host_roundtrip(self, src: np.ndarray) -> np.ndarray:
+        """src -> device -> a fresh host array through the library's pageable-buffer copy paths."""
+        src = np.ascontiguousarray(src)
+        dst = np.empty_like(src)
+        self._check(self.L.s3d_host_roundtrip(self.h, src.ctypes.data, dst.ctypes.data, src.nbytes),
+                    "host_roundtrip")
+        return dst
 
     def set_option(self, name: str, value: int):
         self._check(self.L.s3d_set_option(self.h, name.encode(), int(value)), f"set_option {name}")

@@ -3,7 +3,7 @@ the chunk-at-a-time parallel memcpy (copy_pipe=0) against the whole-chunk worker
 (copy_pipe=1, host_pipe.h) for several chunk sizes / ring depths.  Through the C API, like a stock
 caller: SIFT3D_detect_keypoints + SIFT3D_extract_descriptors on a 512^3 malloc'ed volume, and
 SIFT3D_extract_dense_descriptors on 256^3.  Results must be bit-identical between the variants.
-Usage: copy_pipe_ab.py [n] [dense_n] [reps]"""
+Usage: copy_pipe_ab.py [n] [dense_n] [reps] [variants: comma list of name=value sets joined by +]"""
 import ctypes as C
 import hashlib
 import sys
@@ -24,7 +24,7 @@ vol = blob_volume_torch((n, n, n), 1234, dev).cpu().numpy().copy()   # pageable
 dvol = blob_volume_torch((dn, dn, dn), 1234, dev).cpu().numpy().copy()
 lib = capi.load_b200()
 cu = bind_cuda(capi)
-variants = ["copy_pipe=0", "copy_pipe=1+pipe_chunk_kb=4096+pipe_slots=8", "copy_pipe=1+pipe_chunk_kb=2048+pipe_slots=16",
+variants = sys.argv[4].split(",") if len(sys.argv) > 4 else ["copy_pipe=0", "copy_pipe=1+pipe_chunk_kb=4096+pipe_slots=8", "copy_pipe=1+pipe_chunk_kb=2048+pipe_slots=16",
             "copy_pipe=1+pipe_chunk_kb=1024+pipe_slots=16", "copy_pipe=1+pipe_chunk_kb=8192+pipe_slots=4",
             "copy_pipe=1+pipe_chunk_kb=1024+pipe_slots=48", "copy_pipe=1+pipe_chunk_kb=16384+pipe_slots=3"]
 
