@@ -827,8 +827,13 @@ static int pipe_ensure(s3d_engine *e, size_t bytes, size_t ns)
 // dir 1 = device -> pageable host.  Returns with the transfer complete.
 static int pipe_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t bytes)
 {
-    const size_t ch = (size_t)std::max(256, e->opt_pipe_chunk_kb) << 10;
-    const size_t ns = (size_t)std::min(64, std::max(2, e->opt_pipe_slots));
+    // Ring geometry: 16 slots of 2 MB measured best on one GPU (tools/copy_pipe_ab.py); with
+    // several ranks on the host the ring shrinks to 8 x 1 MB so that the rings of all ranks stay
+    // inside the last-level cache together, and the polling caller replaces one worker.
+    HostTeam &team = HostTeam::get();
+    const bool shared_host = team.ranks_on_host() > 1;
+    const size_t ch = (size_t)(e->opt_pipe_chunk_kb > 0 ? std::max(256, e->opt_pipe_chunk_kb) : (shared_host ? 1024 : 2048)) << 10;
+    const size_t ns = (size_t)(e->opt_pipe_slots > 0 ? std::min(64, std::max(2, e->opt_pipe_slots)) : (shared_host ? 8 : 16));
     if (pipe_ensure(e, ch * ns, ns)) return -1;
     PipeJob J;
     J.dir = dir;
@@ -858,7 +863,7 @@ static int pipe_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t b
         ce = q;
         return -1;
     };
-    s3d_pipe_run(J, issue, poll);
+    s3d_pipe_run(J, issue, poll, shared_host && team.workers() > 1 ? 1u : 0u);
     const cudaError_t cs = cudaStreamSynchronize(st);  // the last DMAs; the ring is free again
     cudaGetLastError();  // cudaErrorNotReady of the polls is not an error
     if (ce == cudaSuccess) ce = cs;

@@ -31,6 +31,7 @@ public:
         return t;
     }
     unsigned workers() const { return (unsigned)workers_.size(); }
+    unsigned ranks_on_host() const { return share_; }  // $LOCAL_WORLD_SIZE (1 when not set)
     // Runs fn(t) on the workers t = first .. workers() - 1 while the caller runs main_fn();
     // returns when all of them are done.  One job at a time (engines share the team).
     void run(unsigned first, const std::function<void(unsigned)> &job, const std::function<void()> &main_fn)
@@ -70,6 +71,7 @@ private:
         if (hw < 1) hw = 1;
         unsigned share = 1;
         if (const char *v = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(v));
+        share_ = share;
         unsigned n = std::max(2u, std::min(8u, hw / share));  // measured on a 16-core host: 8 beats 16
         if (const char *v = getenv("S3D_COPY_THREADS")) n = (unsigned)std::max(1, atoi(v));
         for (unsigned t = 0; t < n; t++) workers_.emplace_back([this, t] { loop(t); });
@@ -108,6 +110,7 @@ private:
     bool stop_ = false;
     const std::function<void(unsigned)> *job_ = nullptr;
     unsigned first_ = 0;
+    unsigned share_ = 1;
 };
 
 // The chunk pipeline between pageable host memory and a ring of pinned slots.  The parallel
@@ -159,7 +162,7 @@ inline void pipe_worker(PipeJob &J)
 // flight (0) or failed (-1).  The workers of the team run pipe_worker meanwhile.  Returns false
 // when issue / poll reported an error (the workers have left the job by then).
 template <class Issue, class Poll>
-inline bool s3d_pipe_run(PipeJob &J, Issue &&issue, Poll &&poll)
+inline bool s3d_pipe_run(PipeJob &J, Issue &&issue, Poll &&poll, unsigned first_worker = 0)
 {
     bool ok = true;
     auto idle = [](unsigned &spins) {
@@ -226,8 +229,8 @@ inline bool s3d_pipe_run(PipeJob &J, Issue &&issue, Poll &&poll)
         }
         if (!ok) J.abort.store(1);
     };
-    if (J.dir == 0) HostTeam::get().run(0, [&](unsigned) { pipe_worker(J); }, main_up);
-    else HostTeam::get().run(0, [&](unsigned) { pipe_worker(J); }, main_down);
+    if (J.dir == 0) HostTeam::get().run(first_worker, [&](unsigned) { pipe_worker(J); }, main_up);
+    else HostTeam::get().run(first_worker, [&](unsigned) { pipe_worker(J); }, main_down);
     return ok;
 }
 }  // namespace

@@ -1463,7 +1463,6 @@ int sift3d_b200_im_resample(const Image *const src, const double *const units, c
 }
 
 /* ---- functions that lean on libimutil when it is linked (drop-in deployments) */
-extern int write_Mat_rm(const char *path, const Mat_rm *const mat) __attribute__((weak));
 extern int init_im_with_dims(Image *const, const int, const int, const int, const int)
     __attribute__((weak));
 extern int im_pad(const Image *const, Image *const) __attribute__((weak));
@@ -1475,30 +1474,9 @@ extern int draw_lines(const Mat_rm *const, const Mat_rm *const, const int *const
     __attribute__((weak));
 
 static int write_csv(const char *path, const Mat_rm *mat)
-{ /* write_Mat_rm's text format (imutil.c:1343-1421): "%f" fields, ',' separated */
-    const size_t len = strlen(path);
-    FILE *f;
-    int i, j;
-    if (write_Mat_rm) return write_Mat_rm(path, mat);
-    if (len > 3 && strcmp(path + len - 3, ".gz") == 0) {
-        ERR("sift3d_b200: .gz output needs libimutil (write_Mat_rm) to be linked \n");
-        return SIFT3D_FAILURE;
-    }
-    if ((f = fopen(path, "w")) == NULL) return SIFT3D_FAILURE;
-    for (i = 0; i < mat->num_rows; i++)
-        for (j = 0; j < mat->num_cols; j++) {
-            const size_t q = (size_t)i * mat->num_cols + j;
-            if (mat->type == SIFT3D_DOUBLE)
-                fprintf(f, "%f", mat->u.data_double[q]);
-            else if (mat->type == SIFT3D_FLOAT)
-                fprintf(f, "%f", mat->u.data_float[q]);
-            else
-                fprintf(f, "%d", mat->u.data_int[q]);
-            fputc(j < mat->num_cols - 1 ? ',' : '\n', f);
-        }
-    i = ferror(f);
-    fclose(f);
-    return i ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
+{ /* write_Mat_rm's text format (imutil.c:1343-1421), bytes identical to its "%f" / "%d" fields;
+   * formatted in parallel by csv_io.c -- always ours, also when libimutil is linked */
+    return sift3d_b200_write_Mat_rm(path, mat);
 }
 
 int write_Keypoint_store(const char *path, const Keypoint_store *const kp)
