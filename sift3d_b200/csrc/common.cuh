@@ -73,6 +73,9 @@ struct s3d_engine {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H of descriptor chunks behind the kernel
+    cudaStream_t aux_stream = nullptr;   // second compute stream of the chunked descriptor launches
+    int opt_desc_streams = 2;            // host-buffer descriptor call: chunks alternate between 2 streams (1 = one)
+    int opt_desc_chunk = 4096;           // keypoints per chunk of that call (one kernel launch + one D2H copy each)
     std::string err;
     long long launches = 0;
     int blur_mode = 0;

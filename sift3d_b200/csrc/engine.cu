@@ -174,6 +174,7 @@ int s3d_engine_create(s3d_engine **out, int device)
     if (const char *v = getenv("S3D_BLUR_MODE")) e->blur_mode = atoi(v);
     if (const char *v = getenv("S3D_DENSE_COPY")) e->opt_dense_copy = atoi(v);
     if (const char *v = getenv("S3D_COPY_PIPE")) e->opt_copy_pipe = atoi(v);
+    if (const char *v = getenv("S3D_DESC_STREAMS")) e->opt_desc_streams = atoi(v);
     if (const char *v = getenv("S3D_PIPE_CHUNK_KB")) e->opt_pipe_chunk_kb = atoi(v);
     if (const char *v = getenv("S3D_PIPE_SLOTS")) e->opt_pipe_slots = atoi(v);
     if (const char *v = getenv("S3D_DESC_OCC")) e->opt_desc_occ = atoi(v);
@@ -213,6 +214,7 @@ void s3d_engine_destroy(s3d_engine *e)
     for (cudaEvent_t ev : e->slab_ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     delete e;
 }
 
@@ -275,6 +277,8 @@ int s3d_set_option(s3d_engine *e, const char *name, int value)
     else if (!strcmp(name, "pipe_chunk_kb")) e->opt_pipe_chunk_kb = value;
     else if (!strcmp(name, "pipe_slots")) e->opt_pipe_slots = value;
     else if (!strcmp(name, "desc_occ")) e->opt_desc_occ = value;
+    else if (!strcmp(name, "desc_streams")) e->opt_desc_streams = value;
+    else if (!strcmp(name, "desc_chunk")) e->opt_desc_chunk = value;
     else if (!strcmp(name, "desc_norot")) e->opt_desc_norot = value;
     else if (!strcmp(name, "orient_batch")) e->opt_orient_batch = value;
     else if (!strcmp(name, "orient_v1")) e->opt_orient_v1 = value;
@@ -638,18 +642,41 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
     // the host until it is done -- so the copies must be issued AFTER all launches, or chunk
     // i+1's kernel would wait for chunk i's copy.  This way only the last chunk's copy is
     // exposed; the rest leave the device behind the compute.
+    // The chunks' kernels alternate between the engine's stream and a second compute stream:
+    // kernels of one stream run one after the other, and every chunk would end with a tail of
+    // draining CTAs (a keypoint's CTA runs 0.1 ... 0.6 ms, 592 are resident) before the next
+    // chunk starts -- 15 tails per 512^3 volume.  On two streams the next chunk's CTAs fill the
+    // SMs the draining chunk leaves (option "desc_streams", 1 = one stream).
     if (!e->copy_stream) S3D_CUDA(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    const int chunk = 4096;
+    const int chunk = std::max(256, e->opt_desc_chunk);
     const int nchunks = (n + chunk - 1) / chunk;
+    const bool two = e->opt_desc_streams >= 2 && nchunks > 1;
+    cudaStream_t main_stream = e->stream;
+    cudaEvent_t ready = nullptr;
+    if (two) {
+        if (!e->aux_stream) S3D_CUDA(e, cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+        // gradient volumes (first call after a detect) and the keypoint upload happen on the
+        // engine's stream: the second stream starts behind them
+        if (s3d_gradients_prepare(e)) return -1;
+        S3D_CUDA(e, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        if (cudaEventRecord(ready, main_stream) != cudaSuccess ||
+            cudaStreamWaitEvent(e->aux_stream, ready, 0) != cudaSuccess) {
+            cudaEventDestroy(ready);
+            return s3d_fail(e, "descriptor streams", cudaGetLastError(), __FILE__, __LINE__);
+        }
+    }
     std::vector<cudaEvent_t> done(nchunks, nullptr);
     int rc = 0;
     for (int c = 0; c < nchunks && !rc; c++) {
         const int lo = c * chunk, cnt = std::min(chunk, n - lo);
+        cudaStream_t st = two && (c & 1) ? e->aux_stream : main_stream;
+        e->stream = st;
         rc = s3d_k_descriptors(e, e->d_kp_in + lo, cnt, e->d_desc + (size_t)lo * S3D_DESC_STRIDE,
                                kp_levels_only);
+        e->stream = main_stream;
         if (rc) break;
         if (cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventRecord(done[c], e->stream) != cudaSuccess)
+            cudaEventRecord(done[c], st) != cudaSuccess)
             rc = s3d_fail(e, "descriptor events", cudaGetLastError(), __FILE__, __LINE__);
     }
     for (int c = 0; c < nchunks && !rc; c++) {
@@ -660,7 +687,12 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
                             cudaMemcpyDeviceToHost, e->copy_stream) != cudaSuccess)
             rc = s3d_fail(e, "descriptor download", cudaGetLastError(), __FILE__, __LINE__);
     }
-    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    cudaError_t ce = cudaStreamSynchronize(main_stream);
+    if (two) {  // later work on the engine's stream is ordered behind the second stream's chunks
+        const cudaError_t ca = cudaStreamSynchronize(e->aux_stream);
+        if (ce == cudaSuccess) ce = ca;
+        cudaEventDestroy(ready);
+    }
     cudaError_t ce2 = cudaStreamSynchronize(e->copy_stream);
     for (int c = 0; c < nchunks; c++)
         if (done[c]) cudaEventDestroy(done[c]);

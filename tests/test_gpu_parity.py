@@ -483,3 +483,38 @@ def test_pageable_copy_paths_deliver_the_exact_bytes():
                 assert np.array_equal(got, src), (pipe, kb, slots, src.nbytes)
     finally:
         e.close()
+
+
+def test_descriptor_chunks_on_two_streams_agree(b200_lib):
+    """SIFT3D_extract_descriptors (sift.c:2025) queues its keypoints in chunks -- one kernel launch
+    and one D2H copy each -- alternating between two compute streams (options desc_streams,
+    desc_chunk).  The result cannot depend on the chunking or on which stream ran a chunk:
+    bit-identical descriptor stores for one stream / two streams and chunks of 256 ... 4096
+    keypoints, incl. a chunk size that leaves a ragged last chunk, repeated calls, and a call
+    right after a new detect (gradient volumes prepared behind the first chunk)."""
+    from sift3d_b200 import capi
+    cu = C.CDLL(str(capi.CUDA_LIB))
+    cu.s3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    b200_lib.lib.sift3d_b200_engine.restype = C.c_void_p
+    b200_lib.lib.sift3d_b200_engine.argtypes = [C.POINTER(capi.SIFT3D)]
+    vol = np.random.default_rng(9).random((72, 80, 96), dtype=np.float32)   # keypoint-dense
+    with capi.Sift3D(b200_lib, peak_thresh=0.03, corner_thresh=0.2) as s:
+        kp = s.detect_keypoints(vol)
+        assert len(kp) > 1200, len(kp)
+        eng = b200_lib.lib.sift3d_b200_engine(C.byref(s.s))
+        want = None
+        try:
+            for streams, chunk in ((1, 4096), (2, 4096), (2, 256), (1, 256), (2, 300), (2, 1024), (2, 257)):
+                assert cu.s3d_set_option(eng, b"desc_streams", streams) == 0
+                assert cu.s3d_set_option(eng, b"desc_chunk", chunk) == 0
+                if chunk == 300:
+                    s.detect_keypoints(vol)   # fresh pyramid: the gradient volumes are rebuilt
+                for rep in range(2):
+                    d = s.extract_descriptors()
+                    if want is None:
+                        want = d.copy()
+                    assert np.array_equal(d["hists"], want["hists"]), (streams, chunk, rep)
+                    assert np.array_equal(d["xd"], want["xd"])
+        finally:
+            cu.s3d_set_option(eng, b"desc_streams", 2)
+            cu.s3d_set_option(eng, b"desc_chunk", 4096)
