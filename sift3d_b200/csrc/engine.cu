@@ -608,6 +608,8 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
     if (e->noct < 1)
         return s3d_fail(e, "s3d_extract_descriptors: no pyramid", cudaSuccess, __FILE__, __LINE__);
     int kp_levels_only = 1;  // every keypoint on a level s = 0..K-1 (those have gradient volumes)
+    size_t memo_lv = (size_t)-1;  // detector keypoints of a level share sd: test each (level, sd) once
+    double memo_sd = 0.0;
     for (int i = 0; i < n; i++) {
         if (kp[i].o < 0 || kp[i].o >= e->noct || kp[i].s < e->first_level ||
             kp[i].s > e->first_level + e->nlev_g - 1)
@@ -616,8 +618,11 @@ int s3d_extract_descriptors(s3d_engine *e, const s3d_keypoint *kp, int n, void *
         if (kp[i].s < 0 || kp[i].s >= e->K) kp_levels_only = 0;
         if (kp_levels_only) {
             const size_t lv = (size_t)kp[i].o * e->nlev_g + (kp[i].s - e->first_level);
-            const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
-            if (!s3d_desc_window_fine(kp[i].sd, g.ux, g.uy, g.uz)) kp_levels_only = 0;
+            if (lv != memo_lv || kp[i].sd != memo_sd) {
+                const s3d_geom &g = e->slab.empty() ? e->g[lv].g : e->slab_g[lv];
+                if (!s3d_desc_window_fine(kp[i].sd, g.ux, g.uy, g.uz)) kp_levels_only = 0;
+                memo_lv = lv, memo_sd = kp[i].sd;
+            }
         }
     }
     if (n > e->kp_in_cap) {
