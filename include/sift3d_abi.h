@@ -239,6 +239,30 @@ int sift3d_b200_materialize_pyramids(SIFT3D *sift3d);
 void *sift3d_b200_engine(const SIFT3D *sift3d);
 /* Number of candidates found by the last detect (before orientation rejection). */
 int sift3d_b200_num_candidates(const SIFT3D *sift3d);
+/* SIFT3D_detect_keypoints (sift.c:1609) for ONE volume Z-slab tiled over several GPUs
+ * (BASELINE.json configs[4]): `im` holds this rank's planes [zsplit[r], zsplit[r+1]), `comm` is
+ * an s3d_comm* (include/sift3d_cuda.h).  Collective; keypoints come back in global coordinates,
+ * in the reference's scan order within the rank.  INTEGRATION.md section 5. */
+int SIFT3D_detect_keypoints_slab(SIFT3D *const sift3d, const Image *const im, const int *zsplit,
+                                 void *comm, Keypoint_store *const kp);
+/* im_inv_transform with an Affine (imutil.c:2040-2083; A = the 3 x 4 matrix, row-major; interp:
+ * 0 = LINEAR, 1 = LANCZOS2 as in interp_type, imtypes.h:105-108) and im_resample
+ * (imutil.c:2191-2244) on the device.  SURVEY.md 8f N3. */
+int sift3d_b200_im_inv_transform_affine(const double A[12], const Image *const src, const int interp,
+                                        const int resize, Image *const dst);
+int sift3d_b200_im_resample(const Image *const src, const double *const units, const int interp,
+                            Image *const dst);
+/* write_Mat_rm (imutil.c:1343-1421), .csv or .csv.gz: the bytes the reference writes, rows
+ * formatted in parallel (host/csv_io.c; write_Keypoint_store / write_SIFT3D_Descriptor_store sit
+ * on it).  sift3d_b200_format_f: the characters of printf("%f", v) -- at most 352, no
+ * terminator -- and their count.  SURVEY.md 8f N2. */
+int sift3d_b200_write_Mat_rm(const char *path, const Mat_rm *const mat);
+int sift3d_b200_format_f(char *dst, double v);
+/* Host-side Gaussian tap design (init_Gauss_filter imutil.c:3657-3710,
+ * init_Gauss_incremental_filter imutil.c:3713-3734): f64 design, f32 normalisation.  The caller
+ * frees g->f.kernel. */
+int s3dh_gauss_filter(Gauss_filter *g, double sigma, int dim);
+int s3dh_gauss_incremental(Gauss_filter *g, double s_cur, double s_next, int dim);
 
 #ifdef __cplusplus
 }
