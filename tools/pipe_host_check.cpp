@@ -67,7 +67,7 @@ struct MockDma {
     }
 };
 
-int run_case(int dir, size_t bytes, size_t ch, size_t ns, unsigned delay_us, unsigned seed)
+int run_case(int dir, size_t bytes, size_t ch, size_t ns, unsigned delay_us, unsigned seed, unsigned first_worker)
 {
     std::vector<char> host(bytes), dev(bytes), slots(ch * ns), want(bytes);
     std::mt19937 rng(seed);
@@ -101,7 +101,7 @@ int run_case(int dir, size_t bytes, size_t ch, size_t ns, unsigned delay_us, uns
             return true;
         };
         auto poll = [&](size_t c) { return ev[c % ns].load(std::memory_order_acquire) ? 1 : 0; };
-        if (!s3d_pipe_run(J, issue, poll)) bad++;
+        if (!s3d_pipe_run(J, issue, poll, first_worker)) bad++;
         // cudaStreamSynchronize: the queue drains before the transfer returns
         for (size_t s = 0; s < ns; s++)
             while (!ev[s].load(std::memory_order_acquire)) std::this_thread::yield();
@@ -126,7 +126,9 @@ int main()
                 for (size_t bytes : sizes) {
                     if (bytes > ((size_t)48 << 20)) continue;
                     const unsigned delay = ch <= 65536 ? (cases % 3 == 0 ? 0 : 30) : 0;
-                    const int b = run_case(dir, bytes, ch, ns, delay, 1000 + cases);
+                    // several ranks on a host: the polling caller replaces worker 0 (engine.cu)
+                    const unsigned first = HostTeam::get().workers() > 1 ? (unsigned)(cases & 1) : 0u;
+                    const int b = run_case(dir, bytes, ch, ns, delay, 1000 + cases, first);
                     if (b) printf("FAIL dir %d bytes %zu ch %zu ns %zu\n", dir, bytes, ch, ns);
                     bad += b;
                     cases++;
