@@ -161,7 +161,8 @@ struct s3d_engine {
     void *pipe_buf = nullptr;
     size_t pipe_cap = 0;
     std::vector<cudaEvent_t> pipe_ev;
-    int opt_copy_pipe = 1;        // 1 = whole-chunk workers through a ring of small pinned slots (0: round 2's chunk-at-a-time copy)
+    int opt_copy_pipe = -1;       // 1 = whole-chunk workers through a ring of small pinned slots, 0 = round 2's chunk-at-a-time copy,
+                                  // -1 = automatic: the pipeline unless several ranks share the host ($LOCAL_WORLD_SIZE > 1)
     int opt_pipe_chunk_kb = 0;    // 0 = automatic (2048; 1024 with several ranks on the host)
     int opt_pipe_slots = 0;       // 0 = automatic (16; 8 with several ranks on the host)
 

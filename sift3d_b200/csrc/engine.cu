@@ -908,6 +908,19 @@ static int pipe_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t b
     return 0;
 }
 
+// Which staged path a >= 32 MB copy takes (option "copy_pipe": 1 / 0 force one, -1 = automatic).
+// The pipeline keeps one thread busy issuing and polling, which pays when the team is large:
+// measured on a 16-core host (profiles/r02_copy_pipe_ab.txt), 8 threads: dense 256^3 call
+// 30.7 -> 28.2 ms, 512^3 upload equal; but with the 4 / 2 threads a rank gets when 4 / 8 ranks
+// share that host ($LOCAL_WORLD_SIZE) the 512^3 detect call took 37.8 / 73.4 ms against 33.3 /
+// 44.9 ms for the chunk-at-a-time copy, where the caller copies too.  So: pipeline when the
+// process has the host to itself, chunk-at-a-time copy when ranks share it.
+static bool use_copy_pipe(const s3d_engine *e)
+{
+    if (e->opt_copy_pipe >= 0) return e->opt_copy_pipe != 0;
+    return HostTeam::get().ranks_on_host() == 1;
+}
+
 // Device -> PAGEABLE host memory (the caller's malloc'ed Image, SURVEY.md 8b ownership rule).
 // A plain cudaMemcpy stages through the driver's bounce buffer and copies out on one core; here
 // the DMA lands in a ring of two pinned buffers and a team of host threads copies each chunk
@@ -921,7 +934,7 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));
         return 0;
     }
-    if (e->opt_copy_pipe) return pipe_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
+    if (use_copy_pipe(e)) return pipe_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
@@ -955,7 +968,7 @@ static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes
         S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
         return 0;
     }
-    if (e->opt_copy_pipe) return pipe_transfer(e, 0, dev, const_cast<void *>(host), bytes);
+    if (use_copy_pipe(e)) return pipe_transfer(e, 0, dev, const_cast<void *>(host), bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
