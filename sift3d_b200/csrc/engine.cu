@@ -209,6 +209,7 @@ void s3d_engine_destroy(s3d_engine *e)
         if (p) cudaFreeHost(p);
     if (e->pipe_buf) cudaFreeHost(e->pipe_buf);
     for (cudaEvent_t ev : e->pipe_ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : e->pipe_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : e->dense_ev)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->slab_ev) cudaEventDestroy(ev);
@@ -908,6 +909,58 @@ static int pipe_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t b
     return 0;
 }
 
+// The pipeline without a polling thread (host_pipe.h: Pipe2Job; option copy_pipe = 2): every
+// participant has its own stream, two pinned slots and two events.
+static int pipe2_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t bytes)
+{
+    HostTeam &team = HostTeam::get();
+    const unsigned P = team.workers() + 1;
+    const size_t ch = (size_t)(e->opt_pipe_chunk_kb > 0 ? std::max(256, e->opt_pipe_chunk_kb)
+                                                         : (team.ranks_on_host() > 1 ? 1024 : 2048)) << 10;
+    if (pipe_ensure(e, ch * 2 * P, 2 * P)) return -1;
+    while (e->pipe_streams.size() < P) {
+        cudaStream_t st = nullptr;
+        S3D_CUDA(e, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        e->pipe_streams.push_back(st);
+    }
+    // the device buffer is produced / last read on the engine's stream
+    S3D_CUDA(e, cudaStreamSynchronize(e->stream));
+    Pipe2Job J;
+    J.dir = dir;
+    J.host = (char *)host;
+    J.slots = (char *)e->pipe_buf;
+    J.bytes = bytes, J.ch = ch;
+    J.nch = (bytes + ch - 1) / ch;
+    std::atomic<int> first_err{0};
+    auto note = [&](cudaError_t ce) {
+        int zero = 0;
+        if (ce != cudaSuccess) first_err.compare_exchange_strong(zero, (int)ce);
+        return ce == cudaSuccess;
+    };
+    const int device = e->device;
+    auto enter = [&](unsigned) { return note(cudaSetDevice(device)); };
+    auto issue = [&](unsigned p, size_t c, int k) {
+        char *slot = J.slots + (size_t)(2 * p + k) * ch;
+        char *d = (char *)dev + c * ch;
+        const size_t len = std::min(ch, bytes - c * ch);
+        cudaStream_t st = e->pipe_streams[p];
+        if (!note(dir == 0 ? cudaMemcpyAsync(d, slot, len, cudaMemcpyHostToDevice, st)
+                           : cudaMemcpyAsync(slot, d, len, cudaMemcpyDeviceToHost, st)))
+            return false;
+        return note(cudaEventRecord(e->pipe_ev[2 * p + k], st));
+    };
+    auto wait = [&](unsigned p, int k) { return note(cudaEventSynchronize(e->pipe_ev[2 * p + k])); };
+    const bool ok = s3d_pipe2_run(J, enter, issue, wait);
+    cudaError_t ce = ok ? cudaSuccess : (cudaError_t)first_err.load();
+    for (unsigned p = 0; p < P; p++) {  // join: the last DMAs of every participant
+        const cudaError_t cs = cudaStreamSynchronize(e->pipe_streams[p]);
+        if (ce == cudaSuccess) ce = cs;
+    }
+    if (!ok && ce == cudaSuccess) ce = cudaErrorUnknown;
+    if (ce != cudaSuccess) return s3d_fail(e, dir ? "pipelined download" : "pipelined upload", ce, __FILE__, __LINE__);
+    return 0;
+}
+
 // Which staged path a >= 32 MB copy takes (option "copy_pipe": 1 / 0 force one, -1 = automatic).
 // The pipeline keeps one thread busy issuing and polling, which pays when the team is large:
 // measured on a 16-core host (profiles/r02_copy_pipe_ab.txt), 8 threads: dense 256^3 call
@@ -934,6 +987,7 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));
         return 0;
     }
+    if (e->opt_copy_pipe == 2) return pipe2_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
     if (use_copy_pipe(e)) return pipe_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -968,6 +1022,7 @@ static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes
         S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
         return 0;
     }
+    if (e->opt_copy_pipe == 2) return pipe2_transfer(e, 0, dev, const_cast<void *>(host), bytes);
     if (use_copy_pipe(e)) return pipe_transfer(e, 0, dev, const_cast<void *>(host), bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};

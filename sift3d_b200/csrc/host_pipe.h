@@ -233,4 +233,83 @@ inline bool s3d_pipe_run(PipeJob &J, Issue &&issue, Poll &&poll, unsigned first_
     else HostTeam::get().run(first_worker, [&](unsigned) { pipe_worker(J); }, main_down);
     return ok;
 }
+// ---- the pipeline without a polling thread (option copy_pipe = 2) -------------------------
+// When several ranks share a host a rank has 2 ... 4 copy threads, and one that only issues and
+// polls is a quarter or half of the copy capacity gone.  Here EVERY participant -- the workers
+// and the caller -- owns two private pinned slots, its own stream and two events, and runs the
+// whole life of its chunks itself: claim a chunk from the atomic counter, wait for the slot's
+// previous DMA, copy, queue the DMA, record the event.  No shared state but the counter.
+//   issue(p, c, k): queue the DMA of chunk c between participant p's slot k and the device on p's
+//                   stream and record the slot's event; false on error
+//   wait(p, k):     block until the DMA last recorded for p's slot k has completed; false on error
+//   enter(p):       called once by participant p on its own thread before anything else
+// The caller is participant workers(); its slots are the last two.  Returns false on error.  The
+// DMAs of an upload may still be in flight on return: the caller joins the streams.
+struct Pipe2Job {
+    int dir = 0;
+    char *host = nullptr;
+    char *slots = nullptr;  // 2 * (workers + 1) slots of ch bytes
+    size_t bytes = 0, ch = 0, nch = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<int> fail{0};
+};
+
+template <class Enter, class Issue, class Wait>
+inline void s3d_pipe2_participant(Pipe2Job &J, unsigned p, Enter &enter, Issue &issue, Wait &wait)
+{
+    if (!enter(p)) {
+        J.fail.store(1);
+        return;
+    }
+    char *slot[2] = {J.slots + (size_t)(2 * p) * J.ch, J.slots + (size_t)(2 * p + 1) * J.ch};
+    auto len_of = [&](size_t c) { return std::min(J.ch, J.bytes - c * J.ch); };
+    int k = 0;
+    if (J.dir == 0) {
+        bool used[2] = {false, false};
+        for (;;) {
+            if (J.fail.load(std::memory_order_relaxed)) return;
+            const size_t c = J.next.fetch_add(1, std::memory_order_relaxed);
+            if (c >= J.nch) return;
+            if (used[k] && !wait(p, k)) break;
+            memcpy(slot[k], J.host + c * J.ch, len_of(c));
+            if (!issue(p, c, k)) break;
+            used[k] = true;
+            k ^= 1;
+        }
+    } else {
+        size_t pend_c[2] = {0, 0};
+        int pend_k[2] = {0, 0}, npend = 0;
+        bool more = true;
+        for (;;) {
+            if (J.fail.load(std::memory_order_relaxed)) return;
+            if (more) {
+                const size_t c = J.next.fetch_add(1, std::memory_order_relaxed);
+                if (c >= J.nch) {
+                    more = false;
+                } else {
+                    if (!issue(p, c, k)) break;
+                    pend_c[npend] = c, pend_k[npend] = k, npend++;
+                    k ^= 1;
+                }
+            }
+            if (npend == 2 || (!more && npend > 0)) {  // the older chunk: wait for it, copy it out
+                if (!wait(p, pend_k[0])) break;
+                memcpy(J.host + pend_c[0] * J.ch, slot[pend_k[0]], len_of(pend_c[0]));
+                pend_c[0] = pend_c[1], pend_k[0] = pend_k[1], npend--;
+            }
+            if (!more && npend == 0) return;
+        }
+    }
+    J.fail.store(1);
+}
+
+template <class Enter, class Issue, class Wait>
+inline bool s3d_pipe2_run(Pipe2Job &J, Enter &&enter, Issue &&issue, Wait &&wait)
+{
+    HostTeam &team = HostTeam::get();
+    const unsigned me = team.workers();
+    team.run(0, [&](unsigned t) { s3d_pipe2_participant(J, t, enter, issue, wait); },
+             [&] { s3d_pipe2_participant(J, me, enter, issue, wait); });
+    return J.fail.load() == 0;
+}
 }  // namespace

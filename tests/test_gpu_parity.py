@@ -463,8 +463,8 @@ def test_orientation_kernels_agree(b200_lib):
 def test_pageable_copy_paths_deliver_the_exact_bytes():
     """The staged copies between a caller's PAGEABLE buffers and the device (im_copy_data of the
     input Image, imutil.c:1895; the dense result in the caller's Image, sift.c:2375-2380): the
-    chunk-at-a-time path and the whole-chunk worker pipeline (option copy_pipe, csrc/host_pipe.h),
-    for sizes below / at / beyond the staging thresholds and rings of different depth.  The CPU
+    chunk-at-a-time path, the whole-chunk worker pipeline and its poller-free variant with one
+    stream per host thread (option copy_pipe = 0 / 1 / 2, csrc/host_pipe.h), for sizes below / at / beyond the staging thresholds and rings of different depth.  The CPU
     check of the pipeline's logic is tests/test_host_pipe.py; this is the same against the real
     DMA engine."""
     from sift3d_b200.engine_api import Engine
@@ -474,7 +474,7 @@ def test_pageable_copy_paths_deliver_the_exact_bytes():
         sizes = [1 << 20, (64 << 20) + 4, (72 << 20) + 12344, (160 << 20) + 8]
         srcs = [rng.integers(0, 2 ** 32, nb // 4, dtype=np.uint32) for nb in sizes]
         for pipe, kb, slots in ((0, 4096, 8), (1, 4096, 8), (1, 1024, 3), (1, 2048, 16), (1, 16384, 2),
-                                (1, 256, 64)):
+                                (1, 256, 64), (2, 1024, 0), (2, 2048, 0), (2, 256, 0), (2, 8192, 0)):
             e.set_option("copy_pipe", pipe)
             e.set_option("pipe_chunk_kb", kb)
             e.set_option("pipe_slots", slots)

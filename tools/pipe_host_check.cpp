@@ -111,6 +111,50 @@ int run_case(int dir, size_t bytes, size_t ch, size_t ns, unsigned delay_us, uns
     if (J.ndone.load() != J.nch) bad++;
     return bad;
 }
+
+// The poller-free pipeline (Pipe2Job): one FIFO "stream" per participant, all served by the one
+// mock DMA thread; an event per (participant, slot).
+int run_case2(int dir, size_t bytes, size_t ch, unsigned delay_us, unsigned seed)
+{
+    const unsigned P = HostTeam::get().workers() + 1;
+    std::vector<char> host(bytes), dev(bytes), slots(ch * 2 * P), want(bytes);
+    std::mt19937 rng(seed);
+    for (size_t i = 0; i < bytes; i++) want[i] = (char)rng();
+    if (dir == 0) host = want, std::fill(dev.begin(), dev.end(), 0x55);
+    else dev = want, std::fill(host.begin(), host.end(), 0x55);
+    std::vector<std::atomic<int>> ev(2 * P);
+    for (auto &x : ev) x.store(1);
+    Pipe2Job J;
+    J.dir = dir;
+    J.host = host.data();
+    J.slots = slots.data();
+    J.bytes = bytes, J.ch = ch;
+    J.nch = (bytes + ch - 1) / ch;
+    std::atomic<int> bad{0};
+    {
+        MockDma dma(delay_us);  // one queue: in order over all participants, a fortiori per participant
+        auto enter = [&](unsigned) { return true; };
+        auto issue = [&](unsigned p, size_t c, int k) {
+            char *slot = J.slots + (size_t)(2 * p + k) * ch;
+            const size_t len = std::min(ch, bytes - c * ch);
+            if (!ev[2 * p + k].load(std::memory_order_acquire)) bad++;  // slot still in flight
+            ev[2 * p + k].store(0, std::memory_order_release);
+            if (dir == 0) dma.push({dev.data() + c * ch, slot, len, &ev[2 * p + k], slot});
+            else dma.push({slot, dev.data() + c * ch, len, &ev[2 * p + k], nullptr});
+            return true;
+        };
+        auto wait = [&](unsigned p, int k) {
+            while (!ev[2 * p + k].load(std::memory_order_acquire)) std::this_thread::yield();
+            return true;
+        };
+        if (!s3d_pipe2_run(J, enter, issue, wait)) bad++;
+        for (auto &x : ev)
+            while (!x.load(std::memory_order_acquire)) std::this_thread::yield();
+    }
+    const std::vector<char> &got = dir == 0 ? dev : host;
+    if (memcmp(got.data(), want.data(), bytes)) bad++;
+    return bad.load();
+}
 }  // namespace
 
 int main()
@@ -134,6 +178,17 @@ int main()
                     cases++;
                 }
             }
+    for (int dir = 0; dir < 2; dir++)
+        for (size_t ch : chs) {
+            const size_t sizes[] = {1, ch - 1, ch, ch + 1, 2 * ch, 2 * ch + 1, 7 * ch - 3, 40 * ch + 17, 200 * ch + 4095};
+            for (size_t bytes : sizes) {
+                if (bytes > ((size_t)48 << 20)) continue;
+                const int b = run_case2(dir, bytes, ch, ch <= 65536 && (cases % 2) ? 20 : 0, 5000 + cases);
+                if (b) printf("FAIL v2 dir %d bytes %zu ch %zu\n", dir, bytes, ch);
+                bad += b;
+                cases++;
+            }
+        }
     // the parallel memcpy of one chunk (HostTeam::copy), odd sizes
     for (size_t len : {(size_t)1, (size_t)4095, (size_t)4097, (size_t)1000003, (size_t)(8 << 20) + 5}) {
         std::vector<char> a(len), b(len, 0);
