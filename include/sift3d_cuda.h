@@ -228,9 +228,10 @@ int s3d_set_blur_mode(s3d_engine *e, int mode);
  * (4: voxels the orientation kernel fetches ahead; 8 = line-aligned batches), "orient_v1" (0; 1 = the thread-per-candidate orientation kernel
  * instead of the grouped one: A/B measurements and tests), "dense_copy" (1: staged parallel copies to/from pageable host memory),
  * "desc_streams" (2: s3d_extract_descriptors queues its 4096-keypoint chunks on two alternating compute streams so that a chunk's draining
- * CTAs overlap the next chunk; 1 = one stream), "desc_chunk" (4096: keypoints per chunk), "copy_pipe" (-1: how those staged copies run: 1 = every host thread moves whole chunks through a ring of "pipe_slots" pinned slots of
- * "pipe_chunk_kb" KB (0 = automatic: 16 x 2048, 8 x 1024 with several ranks on the host; csrc/host_pipe.h), 0 = one chunk at a time split over the
- * threads, -1 = automatic: 1 unless $LOCAL_WORLD_SIZE > 1, where a rank has too few host threads to spare one for issuing and polling),
+ * CTAs overlap the next chunk; 1 = one stream), "desc_chunk" (4096: keypoints per chunk), "copy_pipe" (-1: how those staged copies run: 0 = one chunk at a time split over the host threads, 1 = every thread moves whole chunks
+ * through a ring of "pipe_slots" pinned slots of "pipe_chunk_kb" KB (0 = automatic: 16 x 2048) while the caller issues the DMAs and polls,
+ * 2 = every thread incl. the caller owns a stream and two slots and runs its chunks alone (csrc/host_pipe.h); -1 = automatic: 1, or 2 when
+ * $LOCAL_WORLD_SIZE > 1, where a rank has too few host threads to spare one for polling),
  * "blur_v1" (0; 1 = the round-1 fused Gaussian k_blur_fused (LDG fill) also where the TMA-fed k_blur_tma is eligible: A/B and
  * tests), "blur_rpt4_hw" (3: widest filter half-width that takes k_blur_tma's 64 x 64 tile), "blur_w0" .. "blur_w3" (permille: per-plane cost of a
  * left / right / top / bottom edge column of the fused blur relative to an interior one; balances the persistent CTAs' z ranges). */

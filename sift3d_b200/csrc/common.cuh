@@ -162,8 +162,8 @@ struct s3d_engine {
     size_t pipe_cap = 0;
     std::vector<cudaEvent_t> pipe_ev;
     std::vector<cudaStream_t> pipe_streams;  // copy_pipe = 2: one per participant
-    int opt_copy_pipe = -1;       // 1 = whole-chunk workers through a ring of small pinned slots, 0 = round 2's chunk-at-a-time copy,
-                                  // -1 = automatic: the pipeline unless several ranks share the host ($LOCAL_WORLD_SIZE > 1)
+    int opt_copy_pipe = -1;       // staged copies >= 32 MB: 0 = round 2's chunk-at-a-time copy, 1 = whole-chunk workers + a polling
+                                  // caller, 2 = poller-free (a stream per host thread); -1 = automatic: 1, or 2 when ranks share the host
     int opt_pipe_chunk_kb = 0;    // 0 = automatic (2048; 1024 with several ranks on the host)
     int opt_pipe_slots = 0;       // 0 = automatic (16; 8 with several ranks on the host)
 

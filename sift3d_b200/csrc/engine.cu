@@ -950,7 +950,9 @@ static int pipe2_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t 
         return note(cudaEventRecord(e->pipe_ev[2 * p + k], st));
     };
     auto wait = [&](unsigned p, int k) { return note(cudaEventSynchronize(e->pipe_ev[2 * p + k])); };
-    const bool ok = s3d_pipe2_run(J, enter, issue, wait);
+    // ranks sharing the host: the caller takes worker 0's place, so that a rank runs exactly the
+    // cores / ranks threads the team was sized for
+    const bool ok = s3d_pipe2_run(J, enter, issue, wait, team.ranks_on_host() > 1 && team.workers() > 1 ? 1u : 0u);
     cudaError_t ce = ok ? cudaSuccess : (cudaError_t)first_err.load();
     for (unsigned p = 0; p < P; p++) {  // join: the last DMAs of every participant
         const cudaError_t cs = cudaStreamSynchronize(e->pipe_streams[p]);
@@ -961,17 +963,20 @@ static int pipe2_transfer(s3d_engine *e, int dir, void *dev, void *host, size_t 
     return 0;
 }
 
-// Which staged path a >= 32 MB copy takes (option "copy_pipe": 1 / 0 force one, -1 = automatic).
-// The pipeline keeps one thread busy issuing and polling, which pays when the team is large:
-// measured on a 16-core host (profiles/r02_copy_pipe_ab.txt), 8 threads: dense 256^3 call
-// 30.7 -> 28.2 ms, 512^3 upload equal; but with the 4 / 2 threads a rank gets when 4 / 8 ranks
-// share that host ($LOCAL_WORLD_SIZE) the 512^3 detect call took 37.8 / 73.4 ms against 33.3 /
-// 44.9 ms for the chunk-at-a-time copy, where the caller copies too.  So: pipeline when the
-// process has the host to itself, chunk-at-a-time copy when ranks share it.
-static bool use_copy_pipe(const s3d_engine *e)
+// Which staged path a >= 32 MB copy takes (option "copy_pipe": 0 / 1 / 2 force one, -1 = automatic).
+// Measured on a 16-core host (profiles/r02_copy_pipe_ab.txt).  With the 8 threads a process gets
+// when it has the host to itself, the pipeline with a polling caller (1) and the poller-free one
+// (2) are equal (512^3 detect call 27.5 / 27.9 ms, dense 256^3 call 28.8 / 28.1 ms) and both beat
+// the chunk-at-a-time copy on the dense download (30.7 ms).  With the 4 / 2 threads a rank gets
+// when 4 / 8 ranks share that host ($LOCAL_WORLD_SIZE) a thread that only polls is a quarter /
+// half of the copy capacity: detect 37.8 / 73.4 ms for (1) against 33.3 / 44.9 ms for the
+// chunk-at-a-time copy (0), where the caller copies too -- and 31.3 / 36.7 ms against 42.0 /
+// 40.5 ms (same run) for (2), where everybody copies and nobody meets anybody.  So: (1) alone on
+// the host, (2) when ranks share it.
+static int copy_pipe_mode(const s3d_engine *e)
 {
-    if (e->opt_copy_pipe >= 0) return e->opt_copy_pipe != 0;
-    return HostTeam::get().ranks_on_host() == 1;
+    if (e->opt_copy_pipe >= 0) return e->opt_copy_pipe;
+    return HostTeam::get().ranks_on_host() == 1 ? 1 : 2;
 }
 
 // Device -> PAGEABLE host memory (the caller's malloc'ed Image, SURVEY.md 8b ownership rule).
@@ -987,8 +992,8 @@ static int d2h_pageable(s3d_engine *e, void *dst, const void *dev, size_t bytes)
         S3D_CUDA(e, cudaStreamSynchronize(e->stream));
         return 0;
     }
-    if (e->opt_copy_pipe == 2) return pipe2_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
-    if (use_copy_pipe(e)) return pipe_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
+    if (copy_pipe_mode(e) == 2) return pipe2_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
+    if (copy_pipe_mode(e) == 1) return pipe_transfer(e, 1, const_cast<void *>(dev), dst, bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
@@ -1022,8 +1027,8 @@ static int h2d_pageable(s3d_engine *e, void *dev, const void *host, size_t bytes
         S3D_CUDA(e, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
         return 0;
     }
-    if (e->opt_copy_pipe == 2) return pipe2_transfer(e, 0, dev, const_cast<void *>(host), bytes);
-    if (use_copy_pipe(e)) return pipe_transfer(e, 0, dev, const_cast<void *>(host), bytes);
+    if (copy_pipe_mode(e) == 2) return pipe2_transfer(e, 0, dev, const_cast<void *>(host), bytes);
+    if (copy_pipe_mode(e) == 1) return pipe_transfer(e, 0, dev, const_cast<void *>(host), bytes);
     if (stage_ensure(e, CH)) return -1;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) S3D_CUDA(e, cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));

@@ -304,11 +304,11 @@ inline void s3d_pipe2_participant(Pipe2Job &J, unsigned p, Enter &enter, Issue &
 }
 
 template <class Enter, class Issue, class Wait>
-inline bool s3d_pipe2_run(Pipe2Job &J, Enter &&enter, Issue &&issue, Wait &&wait)
+inline bool s3d_pipe2_run(Pipe2Job &J, Enter &&enter, Issue &&issue, Wait &&wait, unsigned first_worker = 0)
 {
     HostTeam &team = HostTeam::get();
     const unsigned me = team.workers();
-    team.run(0, [&](unsigned t) { s3d_pipe2_participant(J, t, enter, issue, wait); },
+    team.run(first_worker, [&](unsigned t) { s3d_pipe2_participant(J, t, enter, issue, wait); },
              [&] { s3d_pipe2_participant(J, me, enter, issue, wait); });
     return J.fail.load() == 0;
 }

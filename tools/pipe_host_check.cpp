@@ -114,7 +114,7 @@ int run_case(int dir, size_t bytes, size_t ch, size_t ns, unsigned delay_us, uns
 
 // The poller-free pipeline (Pipe2Job): one FIFO "stream" per participant, all served by the one
 // mock DMA thread; an event per (participant, slot).
-int run_case2(int dir, size_t bytes, size_t ch, unsigned delay_us, unsigned seed)
+int run_case2(int dir, size_t bytes, size_t ch, unsigned delay_us, unsigned seed, unsigned first_worker)
 {
     const unsigned P = HostTeam::get().workers() + 1;
     std::vector<char> host(bytes), dev(bytes), slots(ch * 2 * P), want(bytes);
@@ -147,7 +147,7 @@ int run_case2(int dir, size_t bytes, size_t ch, unsigned delay_us, unsigned seed
             while (!ev[2 * p + k].load(std::memory_order_acquire)) std::this_thread::yield();
             return true;
         };
-        if (!s3d_pipe2_run(J, enter, issue, wait)) bad++;
+        if (!s3d_pipe2_run(J, enter, issue, wait, first_worker)) bad++;
         for (auto &x : ev)
             while (!x.load(std::memory_order_acquire)) std::this_thread::yield();
     }
@@ -183,7 +183,8 @@ int main()
             const size_t sizes[] = {1, ch - 1, ch, ch + 1, 2 * ch, 2 * ch + 1, 7 * ch - 3, 40 * ch + 17, 200 * ch + 4095};
             for (size_t bytes : sizes) {
                 if (bytes > ((size_t)48 << 20)) continue;
-                const int b = run_case2(dir, bytes, ch, ch <= 65536 && (cases % 2) ? 20 : 0, 5000 + cases);
+                const int b = run_case2(dir, bytes, ch, ch <= 65536 && (cases % 2) ? 20 : 0, 5000 + cases,
+                                        HostTeam::get().workers() > 1 ? (unsigned)((cases >> 1) & 1) : 0u);
                 if (b) printf("FAIL v2 dir %d bytes %zu ch %zu\n", dir, bytes, ch);
                 bad += b;
                 cases++;
