@@ -11,8 +11,12 @@
  *   v * 10^6 = (M * 10^6) / 2^k is an exact integer division; printf rounds the exact decimal
  *   expansion to nearest, ties to even (glibc, default rounding mode) -- the same q, remainder
  *   and tie rule give the same digits.  Values of 2^63 / 10^6 and above, NaN and Inf go through
- *   snprintf.  (tests/test_csv_io.py: 4*10^6 doubles incl. every tie pattern m / 2^k, denormals,
- *   negative zero, against snprintf; whole files against the compiled reference.)
+ *   snprintf.  (tests/test_csv_io.py: 4*10^6 doubles incl. every tie pattern m / 2^k,
+ *   denormals, negative zero, against snprintf; whole files against the compiled reference.)
+ *
+ * A .csv.gz is written as a sequence of gzip members, one per block, compressed in parallel like
+ * the text is formatted (RFC 1952 2.2: a gzip file is a series of members; zlib's gzread, zcat
+ * and Python's gzip concatenate them).
  */
 #include <errno.h>
 #include <math.h>
@@ -154,53 +158,73 @@ static int format_rows(const Mat_rm *mat, int r0, int r1, Buf *b)
     return 0;
 }
 
+/* One gzip member holding b (windowBits 15 + 16): concatenated members are a valid .gz stream, so
+ * the blocks of a .csv.gz are compressed in parallel like the text is formatted. */
+static int gzip_member(const Buf *b, Buf *out)
+{
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK)
+        return -1;
+    out->len = 0;
+    if (buf_room(out, deflateBound(&zs, (uLong)b->len) + 64)) {
+        deflateEnd(&zs);
+        return -1;
+    }
+    zs.next_in = (Bytef *)b->p;
+    zs.avail_in = (uInt)b->len;
+    zs.next_out = (Bytef *)out->p;
+    zs.avail_out = (uInt)out->cap;
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) {
+        deflateEnd(&zs);
+        return -1;
+    }
+    out->len = out->cap - zs.avail_out;
+    return deflateEnd(&zs) == Z_OK ? 0 : -1;
+}
+
 /* write_Mat_rm (imutil.c:1343-1421): .csv, or .csv.gz through zlib. */
 int sift3d_b200_write_Mat_rm(const char *path, const Mat_rm *const mat)
 {
     const size_t plen = strlen(path);
     const int compress = plen > 3 && strcmp(path + plen - 3, ".gz") == 0;
     FILE *file = NULL;
-    gzFile gz = NULL;
     int fail = 0, nblocks, rows_per_block, blk;
     if (mat->type != SIFT3D_DOUBLE && mat->type != SIFT3D_FLOAT && mat->type != SIFT3D_INT)
         return SIFT3D_FAILURE;
     if (make_parent_dirs(path)) return SIFT3D_FAILURE;
-    if (compress) {
-        if ((gz = gzopen(path, "w")) == NULL) return SIFT3D_FAILURE;
-        gzbuffer(gz, 1 << 20);
-    } else if ((file = fopen(path, "w")) == NULL) {
-        return SIFT3D_FAILURE;
-    }
+    if ((file = fopen(path, "w")) == NULL) return SIFT3D_FAILURE;
     rows_per_block = mat->num_cols > 0 ? 32768 / mat->num_cols : 1;
     if (rows_per_block < 1) rows_per_block = 1;
     nblocks = mat->num_cols > 0 ? (mat->num_rows + rows_per_block - 1) / rows_per_block : 0;
+    if (compress && nblocks == 0) { /* an empty matrix is still a valid (empty) gzip stream */
+        Buf empty = {NULL, 0, 0}, z = {NULL, 0, 0};
+        if (gzip_member(&empty, &z) || fwrite(z.p, 1, z.len, file) != z.len) fail = 1;
+        free(z.p);
+    }
 #pragma omp parallel
     {
-        Buf b = {NULL, 0, 0};
+        Buf b = {NULL, 0, 0}, z = {NULL, 0, 0};
 #pragma omp for ordered schedule(static, 1)
         for (blk = 0; blk < nblocks; blk++) {
             const int r0 = blk * rows_per_block;
             const int r1 = r0 + rows_per_block < mat->num_rows ? r0 + rows_per_block : mat->num_rows;
-            const int bad = format_rows(mat, r0, r1, &b);
+            int bad = format_rows(mat, r0, r1, &b);
+            const Buf *w = &b;
+            if (!bad && compress) {
+                bad = gzip_member(&b, &z);
+                w = &z;
+            }
 #pragma omp ordered
             {
                 if (bad) fail = 1;
-                else if (!fail) {
-                    if (compress) {
-                        if (gzwrite(gz, b.p, (unsigned)b.len) != (int)b.len) fail = 1;
-                    } else if (fwrite(b.p, 1, b.len, file) != b.len) {
-                        fail = 1;
-                    }
-                }
+                else if (!fail && fwrite(w->p, 1, w->len, file) != w->len) fail = 1;
             }
         }
         free(b.p);
+        free(z.p);
     }
-    if (compress) {
-        if (gzclose(gz) != Z_OK) fail = 1;
-    } else {
-        if (ferror(file)) fail = 1;
-        if (fclose(file) != 0) fail = 1;
-    }
+    if (ferror(file)) fail = 1;
+    if (fclose(file) != 0) fail = 1;
     return fail ? SIFT3D_FAILURE : SIFT3D_SUCCESS;
 }
