@@ -767,6 +767,10 @@ def main():
             "e2e": {"value": nvox * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 4 * nvox, "d2h_bytes_per_step": int(d2h),
                     "source": "pageable (malloc) host volume, as a stock im_read caller has",
+                    "host_copy": (f"staged through pinned slots by min(8, {os.cpu_count()} cores / {world} ranks) host "
+                                  f"threads ({'polling' if world == 1 else 'poller-free'} chunk pipeline, "
+                                  "csrc/host_pipe.h); descriptor chunks of 4096 keypoints alternate between two "
+                                  "compute streams, their D2H copies run behind the next chunks"),
                     "pinned": {"value": nvox * world / (ms_e2e_pin * 1e-3), "ms_per_step": ms_e2e_pin}},
             "gpu_launches": launches,
             "clocks": clocks,
