@@ -64,3 +64,28 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
                         "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env,
                        timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_reference_arm_line_has_the_contract_keys(built):
+    """`bench.py --impl reference` (rank 0): ONE JSON line with the driver's keys, the metric of
+    BASELINE.json, a cpu_baseline describing this run and an e2e object without transfers."""
+    import json
+    import oracle_api
+    if not oracle_api.REF_LIB.exists():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--ref-size", "48"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    base = json.loads((REPO / "BASELINE.json").read_text())
+    assert d["impl"] == "reference" and d["metric"].split(",")[0] in base["metric"]
+    for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"] and "workload" in d["config"]
