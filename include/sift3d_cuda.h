@@ -221,20 +221,35 @@ int s3d_blur_device(s3d_engine *e, const float *dev_src, float *dev_dst, int nx,
                     int nc, const float *taps, int width, double unit, const double units[3]);
 /* 0 = auto (fused fast path when eligible), 1 = force the generic per-axis path. */
 int s3d_set_blur_mode(s3d_engine *e, int mode);
-/* Debug/tuning switches: "icos_fast" (1), "blur_mode" (0), "desc_v1" (0), "desc_path" (0: automatic;
- * 1..3 force one of the descriptor kernel's fixed-point fallback paths, +4 leaves its row intervals
- * untrimmed -- tests only), "desc_occ" (4: CTAs per SM the descriptor kernel is compiled for; 3),
- * "desc_norot" (0; 1 = no lane-dependent vertex order in the descriptor scatter), "orient_batch"
- * (4: voxels the orientation kernel fetches ahead; 8 = line-aligned batches), "orient_v1" (0; 1 = the thread-per-candidate orientation kernel
- * instead of the grouped one: A/B measurements and tests), "dense_copy" (1: staged parallel copies to/from pageable host memory),
- * "desc_streams" (2: s3d_extract_descriptors queues its 4096-keypoint chunks on two alternating compute streams so that a chunk's draining
- * CTAs overlap the next chunk; 1 = one stream), "desc_chunk" (4096: keypoints per chunk), "copy_pipe" (-1: how those staged copies run: 0 = one chunk at a time split over the host threads, 1 = every thread moves whole chunks
- * through a ring of "pipe_slots" pinned slots of "pipe_chunk_kb" KB (0 = automatic: 16 x 2048) while the caller issues the DMAs and polls,
- * 2 = every thread incl. the caller owns a stream and two slots and runs its chunks alone (csrc/host_pipe.h); -1 = automatic: 1, or 2 when
- * $LOCAL_WORLD_SIZE > 1, where a rank has too few host threads to spare one for polling),
- * "blur_v1" (0; 1 = the round-1 fused Gaussian k_blur_fused (LDG fill) also where the TMA-fed k_blur_tma is eligible: A/B and
- * tests), "blur_rpt4_hw" (3: widest filter half-width that takes k_blur_tma's 64 x 64 tile), "blur_w0" .. "blur_w3" (permille: per-plane cost of a
- * left / right / top / bottom edge column of the fused blur relative to an interior one; balances the persistent CTAs' z ranges). */
+/* Debug / tuning switches (name: default -- meaning).  None is needed in production; the A/B
+ * records under profiles/ were taken with them.
+ *   icos_fast: 1, blur_mode: 0, desc_v1: 0 -- literal variants of the kernels
+ *   desc_v2: 0 -- 1 = round 1's descriptor kernel k_descriptor2 instead of k_descriptor3
+ *   desc_path: 0 -- 1..3 force one of the descriptor kernel's fixed-point fallback paths, +4 leaves
+ *       its row intervals untrimmed (tests only)
+ *   desc_occ: 4 -- CTAs per SM the descriptor kernel is compiled for (3)
+ *   desc_pre: 0 -- 1 = the next voxel's gradient is fetched one trip ahead
+ *   desc_norot: 0 -- 1 = no lane-dependent vertex order in k_descriptor2's scatter
+ *   desc_streams: 2 -- s3d_extract_descriptors queues its chunks on two alternating compute
+ *       streams, so that a chunk's draining CTAs overlap the next chunk; 1 = one stream
+ *   desc_chunk: 4096 -- keypoints per chunk of that call (one launch + one D2H copy each)
+ *   orient_v1: 0 -- 1 = the thread-per-candidate orientation kernel instead of the grouped one
+ *   orient_batch: 4, orient_g: 8, orient_scalar: 0 -- variants of the orientation kernels
+ *   dense_copy: 1 -- staged parallel copies to / from pageable host memory (0 = plain cudaMemcpy)
+ *   copy_pipe: -1 -- how those staged copies run: 0 = one chunk at a time split over the host
+ *       threads; 1 = every thread moves whole chunks through a ring of pipe_slots pinned slots of
+ *       pipe_chunk_kb KB (0 = automatic: 16 x 2048) while the caller issues the DMAs and polls;
+ *       2 = every thread incl. the caller owns a stream and two slots and runs its chunks alone
+ *       (csrc/host_pipe.h); -1 = automatic: 1, or 2 when $LOCAL_WORLD_SIZE > 1, where a rank has
+ *       too few host threads to spare one for polling
+ *   blur_v1: 0 -- 1 = round 1's fused Gaussian k_blur_fused (LDG fill) also where the TMA-fed
+ *       k_blur_tma is eligible
+ *   blur_rpt4_hw: 3 -- widest filter half-width that takes k_blur_tma's 64 x 64 tile
+ *   blur_w0 .. blur_w3 -- permille: per-plane cost of a left / right / top / bottom edge column of
+ *       the fused blur relative to an interior one (balances the persistent CTAs' z ranges)
+ *   blur_slabs: 0 -- z slabs the fused blur's work list is ordered by (0 = automatic)
+ *   slab_timing: 0 -- 1 = CUDA-event times of the halo exchanges (s3d_slab_stats)
+ *   blur_dbg, blur_flags -- per-CTA clocks of the last fused blur / experiment flags */
 int s3d_set_option(s3d_engine *e, const char *name, int value);
 /* Debug: per-CTA {start, end clock, SM id, steps} of the last fused blur (after option "blur_dbg"). */
 int s3d_debug_read(s3d_engine *e, void *host, size_t bytes);
