@@ -36,3 +36,15 @@ def test_chunk_pipeline_against_a_mock_dma_engine(exe, threads):
     r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert f"workers {threads}, ok" in r.stdout
+
+
+def test_team_size_follows_the_ranks_on_the_host(exe):
+    """One team per process: min(8, cores / $LOCAL_WORLD_SIZE) threads, at least 2 (torchrun sets
+    the variable; a rank on a shared host then takes the poller-free pipeline, engine.cu)."""
+    cores = os.cpu_count() or 1
+    for ranks in (1, 2, 8):
+        env = {k: v for k, v in os.environ.items() if k != "S3D_COPY_THREADS"}
+        env["LOCAL_WORLD_SIZE"] = str(ranks)
+        r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=600)
+        want = max(2, min(8, cores // ranks))
+        assert r.returncode == 0 and f"workers {want}, ok" in r.stdout, (ranks, r.stdout[-500:])
