@@ -1,6 +1,14 @@
 // host_pipe.h -- host threads for the copies between PAGEABLE host memory and the device
-// (engine.cu).  Plain C++ (no CUDA): tools/pipe_host_check.cpp runs the chunk pipeline against
-// a mock DMA engine on the CPU (tests/test_host_pipe.py).
+// (engine.cu): the caller's Image goes up (im_copy_data, imutil.c:1895) and results come down
+// into the caller's malloc memory (the reference's ownership contract), so every large transfer
+// is staged through pinned memory.  Three ways, option "copy_pipe" of include/sift3d_cuda.h:
+//   0  HostTeam::copy    one chunk at a time, split over the team and the caller
+//   1  PipeJob           workers move whole chunks through a ring of slots, the caller issues the
+//                        DMAs and polls (the default when the process has the host to itself)
+//   2  Pipe2Job          everybody owns a stream and two slots and runs its chunks alone (the
+//                        default when ranks share the host)
+// Plain C++ (no CUDA): tools/pipe_host_check.cpp runs both pipelines against a mock DMA engine
+// on the CPU (tests/test_host_pipe.py).
 #pragma once
 
 #include <sched.h>
